@@ -1,0 +1,153 @@
+/*
+ * ramannoodle_b200 — C-ABI of the B200 (sm_100a) MD-Raman hot path.
+ *
+ * The reference (wolearyc/ramannoodle v0.5.0) is pure Python and has no FFI; its plugin
+ * boundary is three ABCs plus one free function (ramannoodle/abstract.py:10-83,
+ * ramannoodle/spectrum/utils.py:12-18).  Each entry point below names the reference
+ * interface it replaces (file:line relative to the reference tree).  The reference-side
+ * binding a maintainer would add (a ctypes stub) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types cross this boundary;
+ *   - all arithmetic is IEEE fp64; arrays are C-contiguous (row-major);
+ *   - `d_` pointers are device pointers on the model's / plan's device, `h_` are host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); device
+ *     entry points enqueue work and return without synchronising;
+ *   - every function returns RN_OK (0) or a negative rn_status; the message of the last
+ *     failure on the calling thread is available from rn_last_error().
+ */
+#ifndef RAMANNOODLE_B200_H
+#define RAMANNOODLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rn_status {
+    RN_OK = 0,
+    RN_ERR_INVALID_ARGUMENT = -1,
+    RN_ERR_CUDA = -2,
+    RN_ERR_UNSUPPORTED = -3,
+    RN_ERR_OUT_OF_MEMORY = -4
+} rn_status;
+
+/* Flags for rn_model_create. */
+#define RN_MODEL_DEFAULT 0
+/* Evaluate every DOF through the dense DMMA projection + spline epilogue, even DOFs whose
+ * interpolant is a single linear piece (disables the affine collapse; used to benchmark
+ * and cross-check the dense path on ARTModels). */
+#define RN_MODEL_FORCE_DENSE 1
+
+typedef struct rn_model rn_model;
+typedef struct rn_spectrum_plan rn_spectrum_plan;
+
+/* Human-readable message of the last error raised on this thread ("" if none). */
+const char* rn_last_error(void);
+
+/* Library / device probe: writes the CUDA runtime version, the device count and the
+ * compute capability (major*10+minor) of `device`.  Used by the loader to fail loudly. */
+int rn_device_info(int device, int* runtime_version, int* device_count, int* compute_capability,
+                   int* sm_count);
+
+/* ------------------------------------------------------------------------------------
+ * Polarizability model — replaces InterpolationModel / ARTModel evaluation state
+ * (ramannoodle/pmodel/_interpolation.py:110-115; ARTModel inherits, pmodel/_art.py:48).
+ *
+ *   h_ref_positions  (N,3)  fractional positions of the ReferenceStructure
+ *   h_lattice        (3,3)  rows are lattice vectors (Å)   (structure/_reference.py:285)
+ *   h_basis          (J,3N) Cartesian basis vectors, one row per DOF (_cart_basis_vectors)
+ *   h_degree         (J,)   B-spline degree k_j of DOF j    (_interpolations[j].k)
+ *   h_knot_off       (J+1,) knots of DOF j are h_knots[h_knot_off[j] .. h_knot_off[j+1])
+ *   h_coef_off       (J+1,) coefficients of DOF j are rows h_coef_off[j] .. h_coef_off[j+1]
+ *                           of h_coefs, an (sum n_j, 9) array (c reshaped (n_j,3,3)->(n_j,9))
+ *   h_weight         (J,)   1 - mask_j                      (_interpolation.py:242)
+ *   h_ref_polarizability (3,3)
+ * Splines use extrapolate=True semantics (scipy BSpline as called at _interpolation.py:243).
+ * ------------------------------------------------------------------------------------ */
+int rn_model_create(const double* h_ref_positions, int64_t num_atoms, const double* h_lattice,
+                    const double* h_basis, int64_t num_dofs, const int32_t* h_degree,
+                    const int64_t* h_knot_off, const double* h_knots, const int64_t* h_coef_off,
+                    const double* h_coefs, const double* h_weight,
+                    const double* h_ref_polarizability, int device, int flags, rn_model** out);
+int rn_model_destroy(rn_model* model);
+
+/* info[0]=num_atoms, [1]=num_dofs, [2]=DOFs folded into the affine term, [3]=DOFs evaluated by
+ * the dense path, [4]=max spline degree on the dense path, [5]=device, [6]=1 if the TMA
+ * affine kernel is eligible for this model size, [7]=max pieces of any dense-path DOF. */
+int rn_model_info(const rn_model* model, int64_t info[8]);
+
+/* PolarizabilityModel.calc_polarizabilities(positions_batch)  (abstract.py:13-29;
+ * _interpolation.py:191-252): d_positions (S,N,3) fractional -> d_alpha (S,3,3). */
+int rn_calc_polarizabilities(const rn_model* model, const double* d_positions, int64_t num_frames,
+                             double* d_alpha, void* stream);
+
+/* The "displacements already computed" entry BASELINE.json's north_star names
+ * (pmodel.get_polarizability(cart_displacements)): d_cart_displacements (S,3N) in Å as
+ * produced at _interpolation.py:217-223 -> d_alpha (S,3,3)  (= _interpolation.py:233-252). */
+int rn_get_polarizability(const rn_model* model, const double* d_cart_displacements,
+                          int64_t num_frames, double* d_alpha, void* stream);
+
+/* Host-buffer form of rn_calc_polarizabilities: streams h_positions to the device in
+ * chunks (copies overlapped with evaluation).  The result is written to h_alpha (host,
+ * may be NULL) and/or d_alpha (device, may be NULL); at least one must be given.
+ * Synchronous.  Pinned (page-locked) host buffers give full PCIe bandwidth; see
+ * rn_host_register.  chunk_frames <= 0 picks ~64 MiB chunks. */
+int rn_calc_polarizabilities_host(const rn_model* model, const double* h_positions,
+                                  int64_t num_frames, double* h_alpha, double* d_alpha,
+                                  int64_t chunk_frames);
+
+/* Trajectory.__init__ stores apply_pbc(positions_ts) (dynamics/_trajectory.py:45;
+ * structure/utils.py:27: p - p // 1).  Elementwise, in place allowed (d_out == d_in). */
+int rn_apply_pbc(const double* d_in, double* d_out, int64_t count, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * MD Raman spectrum — replaces MDRamanSpectrum.measure (spectrum/_raman.py:241-309) with
+ * calc_signal_spectrum (spectrum/utils.py:95-124) evaluated through the identity
+ *   Re FFT_M(autocorr+(x))[k] = (|FFT_M(x)[k]|^2 + sum x^2) / 2,  M = S - 1,
+ * using an arbitrary-length (Bluestein) FFT written for this library.
+ * A plan owns the FFT work buffers for one series length S on one device.
+ * ------------------------------------------------------------------------------------ */
+int rn_spectrum_plan_create(int64_t num_frames, int device, rn_spectrum_plan** out);
+int rn_spectrum_plan_destroy(rn_spectrum_plan* plan);
+/* Number of output points: ceil((S-1)/2) - 1  (the 0 cm^-1 bin is dropped, _raman.py:299-301). */
+int64_t rn_spectrum_num_points(int64_t num_frames);
+/* d_alpha (S,3,3) -> d_wavenumbers (P,), d_intensities (P,), P = rn_spectrum_num_points(S).
+ * laser_correction / bose_einstein_correction follow _raman.py:13-69,303-307. */
+int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, double timestep_fs,
+                   int laser_correction, double laser_wavelength_nm, int bose_einstein_correction,
+                   double temperature_K, double* d_wavenumbers, double* d_intensities, void* stream);
+/* calc_signal_spectrum(signal, sampling_rate) (spectrum/utils.py:95-124) for one real signal of
+ * length M = S-1 of the plan: outputs ceil(M/2) points (bin 0 included). */
+int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal, double sampling_rate,
+                       double* d_wavenumbers, double* d_intensities, void* stream);
+
+/* convolve_spectrum (spectrum/utils.py:12-73): kind 0 = gaussian, 1 = lorentzian.
+ * d_workspace must hold rn_convolve_workspace_size(K, L) bytes (may be NULL if that is 0). */
+size_t rn_convolve_workspace_size(int64_t num_in, int64_t num_out);
+int rn_convolve_spectrum(const double* d_wavenumbers, const double* d_intensities, int64_t num_in,
+                         int kind, double width, const double* d_out_wavenumbers, int64_t num_out,
+                         double* d_out_intensities, void* d_workspace, void* stream);
+
+/* Page-lock / unlock a caller-owned host buffer (cudaHostRegister) for fast transfers. */
+int rn_host_register(void* h_ptr, size_t bytes);
+int rn_host_unregister(void* h_ptr);
+
+/* Host-only helper (no GPU needed): converts one B-spline (t, c (n,9), k) into the piecewise
+ * polynomial table the kernels evaluate.  out_breaks gets the (pieces-1) interior break
+ * points, out_x0 the expansion point of each piece and out_coefs (pieces, k+1, 9) the local
+ * power-basis coefficients.  Returns the number of pieces, or a negative rn_status.
+ * Capacity: out_breaks/out_x0 need n entries, out_coefs n*(k+1)*9. */
+int rn_bspline_to_pp(const double* h_knots, int num_knots, const double* h_coefs, int degree,
+                     double* out_breaks, double* out_x0, double* out_coefs);
+
+/* Kernel-launch counter (incremented by every kernel this library launches); used by
+ * bench.py for its "gpu_launches" claim. */
+int64_t rn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAMANNOODLE_B200_H */

@@ -1,0 +1,97 @@
+// Shared declarations for the ramannoodle_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/ramannoodle_b200.h"
+
+namespace rn {
+
+// ---- error plumbing ---------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launch_count;
+
+#define RN_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t err__ = (expr);                                                        \
+        if (err__ != cudaSuccess) {                                                        \
+            rn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, \
+                          __LINE__);                                                       \
+            return RN_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define RN_CHECK_ARG(cond, ...)              \
+    do {                                     \
+        if (!(cond)) {                       \
+            rn::set_error(__VA_ARGS__);      \
+            return RN_ERR_INVALID_ARGUMENT;  \
+        }                                    \
+    } while (0)
+
+#define RN_LAUNCHED() (rn::g_launch_count.fetch_add(1, std::memory_order_relaxed))
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+constexpr int kMaxDegree = 5;      // highest spline degree the dense epilogue is compiled for
+constexpr int kAffineWarps = 8;    // consumer warps of the TMA affine kernel
+constexpr int kAffineMaxKP = 12;   // k-step pairs per warp the TMA affine kernel is compiled for
+
+}  // namespace rn
+
+// ---- the model handle ---------------------------------------------------------------
+struct rn_model {
+    int device = 0;
+    int sm_count = 0;
+    int64_t num_atoms = 0;   // N
+    int64_t dim = 0;         // K = 3N
+    int64_t num_dofs = 0;    // J
+    int64_t num_linear = 0;  // DOFs folded into the affine term
+    int64_t num_dense = 0;   // DOFs evaluated by projection + spline epilogue
+    int dense_degree = 0;    // max degree over dense DOFs (piece records are padded to it)
+    int dense_max_pieces = 0;
+    double alpha0[9] = {0};  // ref_polarizability + constant parts of the linear DOFs
+
+    // device tables (all fp64)
+    double* d_ref_wrapped = nullptr;  // (K)   apply_pbc(ref positions)
+    double* d_zero_ref = nullptr;     // (K)   zeros (Cartesian-displacement entry)
+    double* d_g_frac = nullptr;       // (Kg,9) affine term acting on wrapped fractional displacements
+    double* d_g_cart = nullptr;       // (Kg,9) affine term acting on Cartesian displacements
+    double* d_v_frac = nullptr;       // (Jd_pad,Kv) dense basis with the lattice folded in
+    double* d_v_cart = nullptr;       // (Jd_pad,Kv) dense basis, Cartesian
+    int32_t* d_piece_off = nullptr;   // (Jd_pad+1) first piece of each dense DOF
+    double* d_breaks = nullptr;       // interior break points; DOF j owns [piece_off[j]-j, piece_off[j+1]-j-1)
+    double* d_pieces = nullptr;       // (pieces, 1 + 9*(dense_degree+1)): x0 then coefficients c[m][q]
+    int64_t g_rows = 0;               // Kg: rows of the affine tables (K padded)
+    int64_t v_cols = 0;               // Kv: columns of the dense basis (K padded to 16)
+    int64_t dense_pad = 0;            // Jd_pad: dense DOFs padded to the J tile
+    int affine_kp = 0;                // k-step pairs per warp for the TMA affine kernel (0 = ineligible)
+};
+
+namespace rn {
+
+// kernels / launchers implemented in rn_polarizability.cu
+int launch_affine(const rn_model* m, const double* d_in, bool wrap, int64_t num_frames, double* d_alpha,
+                  cudaStream_t stream);
+int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
+                 double* d_alpha, cudaStream_t stream);
+int launch_fill_alpha0(const rn_model* m, int64_t num_frames, double* d_alpha, cudaStream_t stream);
+
+}  // namespace rn

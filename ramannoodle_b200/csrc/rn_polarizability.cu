@@ -1,0 +1,625 @@
+// Polarizability evaluation kernels (sm_100a).
+//
+//   alpha_s = alpha_ref + sum_j (1-mask_j) B_j( v_j . vec(wrap(p_s - p_ref) L) )
+//   (ramannoodle/pmodel/_interpolation.py:191-252, structure/utils.py:110-135,
+//    structure/_reference.py:268-285)
+//
+// Three kernels:
+//   affine_tma_kernel      linear DOFs collapsed to alpha0 + D.G.  Frames are streamed with
+//                          TMA bulk copies (cp.async.bulk) into a 4-stage shared-memory ring;
+//                          8 consumer warps each own a K-slice whose G / reference fragments
+//                          stay in registers; the contraction runs on the FP64 tensor pipe
+//                          (DMMA m8n8k4) for 8 of the 9 tensor components and as DFMA for
+//                          the 9th.  HBM-bound: 24N+72 algorithmic bytes per frame.
+//   affine_generic_kernel  same math, any size/alignment, no staging (fallback + cross-check).
+//   dense_kernel           general splines: cp.async-pipelined DMMA GEMM (frames x 3N)(3N x J)
+//                          with the minimum-image wrap applied while loading A fragments, and
+//                          the piecewise-polynomial spline evaluation + 3x3 reduction fused as
+//                          the epilogue (amplitudes never touch HBM).  FP64-pipe-bound:
+//                          2*3N*J flops per frame.
+#include "rn_common.cuh"
+
+namespace rn {
+
+struct Alpha0 {
+    double v[9];
+};
+
+// wrap(pos - ref) into (-0.5, 0.5]: apply_pbc_displacement(calc_displacement(...)) of the
+// reference (structure/utils.py:46,132-135); ties resolve to +0.5 exactly as `d % 1 > 0.5`.
+__device__ __forceinline__ double wrap_disp(double pos, double ref) {
+    const double d = pos - ref;
+    return d - ceil(d - 0.5);
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------
+// generic affine kernel: one warp per group of 8 frames, A fragments straight from global
+// ------------------------------------------------------------------------------------
+template <bool WRAP>
+__global__ void __launch_bounds__(256) affine_generic_kernel(const double* __restrict__ in,
+                                                             const double* __restrict__ ref,
+                                                             const double* __restrict__ G, int64_t frame_begin,
+                                                             int64_t frame_end, int K, Alpha0 a0,
+                                                             double* __restrict__ alpha) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t groups = (frame_end - frame_begin + 7) / 8;
+    for (int64_t grp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); grp < groups; grp += warps) {
+        const int64_t frame = frame_begin + grp * 8 + g;
+        const bool valid = frame < frame_end;
+        const double* row = in + (valid ? frame : frame_begin) * (int64_t)K;
+        double c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+        for (int e0 = 0; e0 < K; e0 += 4) {
+            const int e = e0 + t;
+            double a = 0, b = 0, b2 = 0;
+            if (e < K) {
+                if (valid) {
+                    a = __ldg(row + e);
+                    if (WRAP) a = wrap_disp(a, __ldg(ref + e));
+                }
+                b = __ldg(G + (int64_t)e * 9 + g);
+                if (g == 0) b2 = __ldg(G + (int64_t)e * 9 + 8);
+            }
+            dmma884(c0, c1, a, b);
+            dmma884(d0, d1, a, b2);
+        }
+        if (valid) {
+            alpha[frame * 9 + 2 * t] = c0 + a0.v[2 * t];
+            alpha[frame * 9 + 2 * t + 1] = c1 + a0.v[2 * t + 1];
+            if (t == 0) alpha[frame * 9 + 8] = d0 + a0.v[8];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// TMA affine kernel
+// ------------------------------------------------------------------------------------
+constexpr int kStages = 4;
+constexpr int kRedStride = 12;  // doubles per (warp, frame) slot in the cross-warp reduction buffer
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// Stage layout: 8 frame rows, each one bulk copy of K doubles, at a stride == 8 (mod 16)
+// doubles so that the LDS.128 fragment loads of two consecutive rows hit disjoint banks.
+// Requires K even (frame rows are then multiples of 16 bytes, as cp.async.bulk needs).
+struct AffineSmemLayout {
+    int row_stride;  // doubles
+    int stage_doubles;
+    size_t bytes;
+};
+
+static AffineSmemLayout affine_layout(int K, int kp) {
+    AffineSmemLayout L;
+    L.row_stride = K + (8 - K % 16 + 16) % 16;
+    const int slack = kAffineWarps * 8 * kp;  // fragment loads may run past the last row (values are masked)
+    L.stage_doubles = 8 * L.row_stride;
+    L.bytes = (size_t)(kStages * L.stage_doubles + slack) * 8 + (size_t)2 * kAffineWarps * 8 * kRedStride * 8 +
+              2 * kStages * 8 + 64;
+    return L;
+}
+
+template <int KP, bool WRAP>
+__global__ void __launch_bounds__((kAffineWarps + 1) * 32, 1)
+    affine_tma_kernel(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ G,
+                      int64_t num_frames, int K, int row_stride, int stage_doubles, Alpha0 a0,
+                      double* __restrict__ alpha) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stages = reinterpret_cast<double*>(smem_raw);
+    const int slack = kAffineWarps * 8 * KP;
+    double* red = stages + kStages * stage_doubles + slack;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2 * kAffineWarps * 8 * kRedStride);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t num_tiles = (num_frames + 7) / 8;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, kAffineWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kAffineWarps) {
+        // ---------------- producer: one lane issues the bulk copies ----------------
+        if (lane == 0) {
+            int64_t i = 0;
+            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
+                const int s = (int)(i % kStages);
+                const uint32_t round = (uint32_t)(i / kStages);
+                if (round > 0) mbar_wait(empty0 + 8 * s, (round - 1) & 1);
+                const int64_t frame0 = tile * 8;
+                const int rows = (int)min((int64_t)8, num_frames - frame0);
+                const uint32_t row_bytes = (uint32_t)K * 8u;
+                mbar_arrive_expect_tx(full0 + 8 * s, row_bytes * rows);
+                const uint32_t dst0 = smem_u32(stages + (size_t)s * stage_doubles);
+                const double* src0 = in + frame0 * (int64_t)K;
+                for (int r = 0; r < rows; r++)
+                    tma_bulk_g2s(dst0 + (uint32_t)(r * row_stride) * 8u, src0 + (int64_t)r * K, row_bytes,
+                                 full0 + 8 * s);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int g = lane >> 2, t = lane & 3;
+    const int kbase = warp * 8 * KP + 2 * t;
+    double refv[KP][2], b8[KP][2], b9[KP][2];
+    uint32_t validmask = 0;
+#pragma unroll
+    for (int p = 0; p < KP; p++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int e = kbase + 8 * p + h;  // tables are zero-padded to kAffineWarps*8*KP rows
+            refv[p][h] = WRAP ? __ldg(ref + e) : 0.0;
+            b8[p][h] = __ldg(G + (int64_t)e * 9 + g);
+            b9[p][h] = __ldg(G + (int64_t)e * 9 + 8);
+            if (e < K) validmask |= 1u << (2 * p + h);
+        }
+    }
+    const int rowoff = g * row_stride + kbase;
+    double* myred = red + ((size_t)warp * 8 + g) * kRedStride;
+
+    int64_t i = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
+        const int s = (int)(i % kStages);
+        mbar_wait(full0 + 8 * s, (uint32_t)(i / kStages) & 1);
+        const double* base = stages + (size_t)s * stage_doubles + rowoff;
+        double c0 = 0, c1 = 0, a9 = 0;
+#pragma unroll
+        for (int p = 0; p < KP; p++) {
+            const double2 v = *reinterpret_cast<const double2*>(base + 8 * p);
+            double a_lo = v.x, a_hi = v.y;
+            if (WRAP) {
+                a_lo = wrap_disp(a_lo, refv[p][0]);
+                a_hi = wrap_disp(a_hi, refv[p][1]);
+            }
+            a_lo = (validmask >> (2 * p)) & 1u ? a_lo : 0.0;
+            a_hi = (validmask >> (2 * p + 1)) & 1u ? a_hi : 0.0;
+            dmma884(c0, c1, a_lo, b8[p][0]);
+            a9 = fma(a_lo, b9[p][0], a9);
+            dmma884(c0, c1, a_hi, b8[p][1]);
+            a9 = fma(a_hi, b9[p][1], a9);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);  // stage may be refilled
+        a9 += __shfl_xor_sync(0xffffffffu, a9, 1);
+        a9 += __shfl_xor_sync(0xffffffffu, a9, 2);
+        double* slot = myred + (size_t)(i & 1) * kAffineWarps * 8 * kRedStride;
+        *reinterpret_cast<double2*>(slot + 2 * t) = make_double2(c0, c1);
+        if (t == 0) slot[8] = a9;
+        asm volatile("bar.sync 1, %0;" ::"n"(kAffineWarps * 32) : "memory");
+        if (threadIdx.x < 72) {
+            const int f = threadIdx.x / 9, q = threadIdx.x % 9;
+            const double* r = red + (size_t)(i & 1) * kAffineWarps * 8 * kRedStride + (size_t)f * kRedStride + q;
+            double sum = 0;
+#pragma unroll
+            for (int w = 0; w < kAffineWarps; w++) sum += r[(size_t)w * 8 * kRedStride];
+            const int64_t frame = tile * 8 + f;
+            if (frame < num_frames) alpha[frame * 9 + q] = sum + a0.v[q];
+        }
+    }
+}
+
+template <bool WRAP>
+static int launch_affine_tma(const rn_model* m, const double* d_in, int64_t frames, double* d_alpha, Alpha0 a0,
+                             cudaStream_t stream) {
+    const int K = (int)m->dim;
+    const AffineSmemLayout L = affine_layout(K, m->affine_kp);
+    const int64_t tiles = (frames + 7) / 8;
+    const int grid = (int)std::min<int64_t>(tiles, m->sm_count);
+    const double* ref = WRAP ? m->d_ref_wrapped : m->d_zero_ref;
+    const double* G = WRAP ? m->d_g_frac : m->d_g_cart;
+#define RN_AFFINE_CASE(KP)                                                                                     \
+    case KP: {                                                                                                 \
+        auto kern = affine_tma_kernel<KP, WRAP>;                                                               \
+        RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));        \
+        kern<<<grid, (kAffineWarps + 1) * 32, L.bytes, stream>>>(d_in, ref, G, frames, K, L.row_stride,         \
+                                                                 L.stage_doubles, a0, d_alpha);                \
+        break;                                                                                                 \
+    }
+    switch (m->affine_kp) {
+        RN_AFFINE_CASE(1)
+        RN_AFFINE_CASE(2)
+        RN_AFFINE_CASE(3)
+        RN_AFFINE_CASE(4)
+        RN_AFFINE_CASE(5)
+        RN_AFFINE_CASE(6)
+        RN_AFFINE_CASE(7)
+        RN_AFFINE_CASE(8)
+        RN_AFFINE_CASE(9)
+        RN_AFFINE_CASE(10)
+        RN_AFFINE_CASE(11)
+        RN_AFFINE_CASE(12)
+        default:
+            set_error("affine TMA kernel not compiled for KP=%d", m->affine_kp);
+            return RN_ERR_UNSUPPORTED;
+    }
+#undef RN_AFFINE_CASE
+    RN_LAUNCHED();
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}
+
+template <bool WRAP>
+static int launch_affine_generic(const rn_model* m, const double* d_in, int64_t begin, int64_t end, double* d_alpha,
+                                 Alpha0 a0, cudaStream_t stream) {
+    if (end <= begin) return RN_OK;
+    const int64_t groups = (end - begin + 7) / 8;
+    const int grid = (int)std::min<int64_t>((groups + 7) / 8, (int64_t)m->sm_count * 8);
+    affine_generic_kernel<WRAP><<<grid, 256, 0, stream>>>(d_in, WRAP ? m->d_ref_wrapped : m->d_zero_ref,
+                                                          WRAP ? m->d_g_frac : m->d_g_cart, begin, end, (int)m->dim, a0,
+                                                          d_alpha);
+    RN_LAUNCHED();
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}
+
+static bool g_force_generic_affine = false;
+
+int launch_affine(const rn_model* m, const double* d_in, bool wrap, int64_t num_frames, double* d_alpha,
+                  cudaStream_t stream) {
+    Alpha0 a0;
+    for (int q = 0; q < 9; q++) a0.v[q] = m->alpha0[q];
+    const int K = (int)m->dim;
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_in) % 16) == 0 && (K % 2 == 0);
+    int64_t tma_frames = 0;
+    if (m->affine_kp > 0 && aligned && !g_force_generic_affine) {
+        tma_frames = num_frames;
+        const AffineSmemLayout L = affine_layout(K, m->affine_kp);
+        if (L.bytes > 227 * 1024) tma_frames = 0;
+    }
+    int rc = RN_OK;
+    if (tma_frames > 0) {
+        rc = wrap ? launch_affine_tma<true>(m, d_in, tma_frames, d_alpha, a0, stream)
+                  : launch_affine_tma<false>(m, d_in, tma_frames, d_alpha, a0, stream);
+        if (rc != RN_OK) return rc;
+    }
+    if (tma_frames < num_frames) {
+        rc = wrap ? launch_affine_generic<true>(m, d_in, tma_frames, num_frames, d_alpha, a0, stream)
+                  : launch_affine_generic<false>(m, d_in, tma_frames, num_frames, d_alpha, a0, stream);
+    }
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------
+// alpha = alpha0 for models without DOFs
+// ------------------------------------------------------------------------------------
+__global__ void fill_alpha0_kernel(int64_t count, Alpha0 a0, double* __restrict__ alpha) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        alpha[i] = a0.v[i % 9];
+}
+
+int launch_fill_alpha0(const rn_model* m, int64_t num_frames, double* d_alpha, cudaStream_t stream) {
+    if (num_frames == 0) return RN_OK;
+    Alpha0 a0;
+    for (int q = 0; q < 9; q++) a0.v[q] = m->alpha0[q];
+    const int64_t count = num_frames * 9;
+    const int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)m->sm_count * 8);
+    fill_alpha0_kernel<<<grid, 256, 0, stream>>>(count, a0, d_alpha);
+    RN_LAUNCHED();
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// dense kernel: DMMA projection + fused spline epilogue
+// ------------------------------------------------------------------------------------
+constexpr int kFT = 128;  // frames per CTA tile (8 warps x 16)
+constexpr int kJT = 64;   // DOFs per J tile
+constexpr int kKC = 16;   // K elements per pipeline chunk
+constexpr int kRS = 20;   // padded smem row stride (doubles): conflict-free fragment loads
+constexpr int kDStages = 3;
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int DEG, bool WRAP, bool ALIGN16>
+__global__ void __launch_bounds__(256, 1)
+    dense_kernel(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ V,
+                 const int32_t* __restrict__ piece_off, const double* __restrict__ breaks,
+                 const double* __restrict__ pieces, int64_t num_frames, int K, int Kv, int Jpad, int accumulate,
+                 Alpha0 a0, double* __restrict__ alpha) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);      // [kDStages][kFT][kRS]
+    double* Bs = As + (size_t)kDStages * kFT * kRS;        // [kDStages][kJT][kRS]
+    constexpr int REC = 1 + 9 * (DEG + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int chunks = Kv / kKC;
+    const int jtiles = Jpad / kJT;
+    const int64_t total = (int64_t)jtiles * chunks;
+    const int64_t num_tiles = (num_frames + kFT - 1) / kFT;
+
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t frame0 = tile * kFT;
+
+        auto issue = [&](int64_t it) {
+            if (it < total) {
+                const int jt = (int)(it / chunks), kc = (int)(it % chunks);
+                const int st = (int)(it % kDStages);
+                double* a_dst = As + (size_t)st * kFT * kRS;
+                double* b_dst = Bs + (size_t)st * kJT * kRS;
+                if (ALIGN16) {
+#pragma unroll
+                    for (int r = 0; r < (kFT * 8) / 256; r++) {
+                        const int idx = threadIdx.x + 256 * r;
+                        const int row = idx >> 3, seg = idx & 7;
+                        const int col = kc * kKC + seg * 2;
+                        const int64_t frame = frame0 + row;
+                        int bytes = 0;
+                        if (frame < num_frames && col < K) bytes = min(16, (K - col) * 8);
+                        const double* src = in + (bytes ? frame * (int64_t)K + col : 0);
+                        cp_async_16(smem_u32(a_dst + row * kRS + seg * 2), src, bytes);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < (kFT * 16) / 256; r++) {
+                        const int idx = threadIdx.x + 256 * r;
+                        const int row = idx >> 4, seg = idx & 15;
+                        const int col = kc * kKC + seg;
+                        const int64_t frame = frame0 + row;
+                        const int bytes = (frame < num_frames && col < K) ? 8 : 0;
+                        const double* src = in + (bytes ? frame * (int64_t)K + col : 0);
+                        cp_async_8(smem_u32(a_dst + row * kRS + seg), src, bytes);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < (kJT * 8) / 256; r++) {
+                    const int idx = threadIdx.x + 256 * r;
+                    const int row = idx >> 3, seg = idx & 7;
+                    const double* src = V + ((int64_t)jt * kJT + row) * Kv + kc * kKC + seg * 2;
+                    cp_async_16(smem_u32(b_dst + row * kRS + seg * 2), src, 16);
+                }
+            }
+            cp_async_commit();
+        };
+
+        double out9[2][9];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int q = 0; q < 9; q++) out9[mt][q] = 0.0;
+        double acc[2][8][2];
+
+        __syncthreads();  // previous tile's smem reads are finished
+        for (int p = 0; p < kDStages - 1; p++) issue(p);
+
+        for (int64_t it = 0; it < total; it++) {
+            const int kc = (int)(it % chunks);
+            if (kc == 0) {
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            }
+            cp_async_wait<kDStages - 2>();
+            __syncthreads();
+            issue(it + kDStages - 1);
+            const int st = (int)(it % kDStages);
+            const double* a_src = As + (size_t)st * kFT * kRS + (warp * 16 + g) * kRS + t;
+            const double* b_src = Bs + (size_t)st * kJT * kRS + g * kRS + t;
+#pragma unroll
+            for (int s = 0; s < kKC / 4; s++) {
+                double a[2];
+                a[0] = a_src[4 * s];
+                a[1] = a_src[8 * kRS + 4 * s];
+                if (WRAP) {
+                    const double r = __ldg(ref + kc * kKC + 4 * s + t);
+                    a[0] = wrap_disp(a[0], r);
+                    a[1] = wrap_disp(a[1], r);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) {
+                    const double b = b_src[nt * 8 * kRS + 4 * s];
+                    dmma884(acc[0][nt][0], acc[0][nt][1], a[0], b);
+                    dmma884(acc[1][nt][0], acc[1][nt][1], a[1], b);
+                }
+            }
+            if (kc == chunks - 1) {
+                // ---- fused epilogue: amplitudes -> piecewise polynomials -> 3x3 partial sums ----
+                const int jt = (int)(it / chunks);
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) {
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const int j = jt * kJT + nt * 8 + 2 * t + c;
+                        const int p0 = __ldg(piece_off + j);
+                        const int np = __ldg(piece_off + j + 1) - p0;
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++) {
+                            const double x = acc[mt][nt][c];
+                            int p = 0;
+                            for (int b = 0; b + 1 < np; b++) p += (x >= __ldg(breaks + p0 + b)) ? 1 : 0;
+                            const double* rec = pieces + (int64_t)(p0 + p) * REC;
+                            const double dx = x - __ldg(rec);
+#pragma unroll
+                            for (int q = 0; q < 9; q++) {
+                                double r = __ldg(rec + 1 + q);
+#pragma unroll
+                                for (int mm = 1; mm <= DEG; mm++) r = fma(r, dx, __ldg(rec + 1 + 9 * mm + q));
+                                out9[mt][q] += r;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+
+        // ---- reduce the 4 lanes that share a frame, then store ----
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            const int64_t frame = frame0 + warp * 16 + mt * 8 + g;
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                double v = out9[mt][q];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                out9[mt][q] = v;
+            }
+            if (frame < num_frames) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) {
+                    if ((q & 3) == t) {
+                        const double base = accumulate ? alpha[frame * 9 + q] : a0.v[q];
+                        alpha[frame * 9 + q] = out9[mt][q] + base;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int DEG>
+static int launch_dense_deg(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
+                            double* d_alpha, cudaStream_t stream) {
+    Alpha0 a0;
+    for (int q = 0; q < 9; q++) a0.v[q] = m->alpha0[q];
+    const int K = (int)m->dim;
+    const bool align16 = (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (K % 2 == 0);
+    const size_t smem = (size_t)kDStages * (kFT + kJT) * kRS * sizeof(double);
+    const int64_t tiles = (num_frames + kFT - 1) / kFT;
+    const int grid = (int)std::min<int64_t>(tiles, m->sm_count);
+    const double* ref = m->d_ref_wrapped;
+    const double* V = wrap ? m->d_v_frac : m->d_v_cart;
+#define RN_DENSE_LAUNCH(W, A)                                                                                  \
+    {                                                                                                          \
+        auto kern = dense_kernel<DEG, W, A>;                                                                   \
+        RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        kern<<<grid, 256, smem, stream>>>(d_in, ref, V, m->d_piece_off, m->d_breaks, m->d_pieces, num_frames, K, \
+                                          (int)m->v_cols, (int)m->dense_pad, accumulate ? 1 : 0, a0, d_alpha); \
+    }
+    if (wrap) {
+        if (align16) RN_DENSE_LAUNCH(true, true) else RN_DENSE_LAUNCH(true, false)
+    } else {
+        if (align16) RN_DENSE_LAUNCH(false, true) else RN_DENSE_LAUNCH(false, false)
+    }
+#undef RN_DENSE_LAUNCH
+    RN_LAUNCHED();
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}
+
+int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
+                 double* d_alpha, cudaStream_t stream) {
+    if (num_frames == 0) return RN_OK;
+    switch (m->dense_degree) {
+        case 0:
+        case 1: return launch_dense_deg<1>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
+        case 2: return launch_dense_deg<2>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
+        case 3: return launch_dense_deg<3>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
+        case 4: return launch_dense_deg<4>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
+        case 5: return launch_dense_deg<5>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
+        default:
+            set_error("dense kernel not compiled for spline degree %d", m->dense_degree);
+            return RN_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+static int eval_common(const rn_model* model, const double* d_in, bool wrap, int64_t num_frames, double* d_alpha,
+                       void* stream) {
+    RN_CHECK_ARG(model != nullptr, "model is null");
+    RN_CHECK_ARG(num_frames >= 0, "num_frames must be non-negative");
+    if (num_frames == 0) return RN_OK;
+    RN_CHECK_ARG(d_in && d_alpha, "null device pointer");
+    DeviceGuard guard(model->device);
+    if (!guard.ok) {
+        set_error("cudaSetDevice(%d) failed", model->device);
+        return RN_ERR_CUDA;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (model->num_dofs == 0) return launch_fill_alpha0(model, num_frames, d_alpha, s);
+    int rc = RN_OK;
+    const bool run_affine = model->num_linear > 0;
+    if (run_affine) {
+        rc = launch_affine(model, d_in, wrap, num_frames, d_alpha, s);
+        if (rc != RN_OK) return rc;
+    }
+    if (model->num_dense > 0) rc = launch_dense(model, d_in, wrap, run_affine, num_frames, d_alpha, s);
+    return rc;
+}
+
+extern "C" int rn_calc_polarizabilities(const rn_model* model, const double* d_positions, int64_t num_frames,
+                                        double* d_alpha, void* stream) {
+    return eval_common(model, d_positions, true, num_frames, d_alpha, stream);
+}
+
+extern "C" int rn_get_polarizability(const rn_model* model, const double* d_cart_displacements, int64_t num_frames,
+                                     double* d_alpha, void* stream) {
+    return eval_common(model, d_cart_displacements, false, num_frames, d_alpha, stream);
+}
+
+// Test hook (not in the public header): route the affine term through the generic kernel.
+extern "C" void rn_debug_force_generic_affine(int on) { rn::g_force_generic_affine = on != 0; }
+
+__global__ void apply_pbc_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t count) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const double p = in[i];
+        out[i] = p - floor(p);  // positions - positions // 1  (structure/utils.py:27)
+    }
+}
+
+extern "C" int rn_apply_pbc(const double* d_in, double* d_out, int64_t count, void* stream) {
+    RN_CHECK_ARG(count >= 0, "count must be non-negative");
+    if (count == 0) return RN_OK;
+    RN_CHECK_ARG(d_in && d_out, "null device pointer");
+    const int grid = (int)std::min<int64_t>((count + 255) / 256, 148 * 16);
+    apply_pbc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, d_out, count);
+    RN_LAUNCHED();
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}

@@ -1,0 +1,126 @@
+"""Molecular-dynamics trajectory — drop-in for ``ramannoodle.dynamics.Trajectory``
+(``ramannoodle/dynamics/_trajectory.py:16-109``).
+
+Host (numpy) trajectories are stored wrapped (``apply_pbc``) like the reference, by default
+in page-locked memory so that ``get_raman_spectrum`` streams them to the GPU at full PCIe
+bandwidth.  A trajectory may also be created from a CUDA tensor, in which case it stays
+resident in HBM (the wrap runs on the device) and evaluation involves no host transfer.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections.abc import Sequence
+
+import numpy as np
+
+from . import _lib
+from .abstract import Dynamics, PolarizabilityModel
+from .exceptions import get_type_error, verify_ndarray_shape
+from .spectrum import MDRamanSpectrum
+
+
+def _is_torch_tensor(obj) -> bool:
+    return type(obj).__module__.startswith("torch") and hasattr(obj, "data_ptr")
+
+
+def apply_pbc(positions):
+    """``ramannoodle/structure/utils.py:13-29``: ``positions - positions // 1`` (host)."""
+    try:
+        return positions - positions // 1
+    except TypeError as exc:
+        raise get_type_error("positions", positions, "ndarray") from exc
+
+
+class Trajectory(Dynamics, Sequence):
+    """Positions time series (S,N,3) (fractional) plus a timestep (fs)."""
+
+    def __init__(self, positions_ts, timestep: float, pin_memory: bool = True) -> None:
+        verify_ndarray_shape("positions_ts", positions_ts, (None, None, 3))
+        try:
+            timestep = float(timestep)
+        except TypeError as exc:
+            raise get_type_error("timestep", timestep, "float") from exc
+        if timestep <= 0:
+            raise ValueError("timestep must be positive")
+        self._timestep = timestep
+        self._pinned_owner = None
+        if _is_torch_tensor(positions_ts):
+            self._positions_ts = self._wrap_device(positions_ts)
+        else:
+            self._positions_ts = self._wrap_host(np.asarray(positions_ts), pin_memory)
+
+    @staticmethod
+    def _wrap_device(tensor):
+        import torch  # pylint: disable=import-outside-toplevel
+
+        if not tensor.is_cuda:
+            return Trajectory._wrap_host(tensor.numpy(), True)
+        data = tensor.to(torch.float64).contiguous()
+        out = torch.empty_like(data)
+        device = int(data.device.index or 0)
+        _lib.require_device(device)
+        with torch.cuda.device(device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            status = _lib.lib().rn_apply_pbc(ctypes.c_void_p(data.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                             data.numel(), stream)
+        _lib.check(status, "rn_apply_pbc")
+        return out
+
+    def _wrap_host(self, positions: np.ndarray, pin_memory: bool) -> np.ndarray:
+        wrapped = None
+        if pin_memory and positions.size > 0:
+            try:
+                import torch  # pylint: disable=import-outside-toplevel
+
+                if torch.cuda.is_available():
+                    owner = torch.empty(positions.shape, dtype=torch.float64, pin_memory=True)
+                    wrapped = owner.numpy()
+                    np.floor_divide(positions, 1, out=wrapped)  # positions // 1
+                    np.subtract(positions, wrapped, out=wrapped)  # positions - positions // 1
+                    self._pinned_owner = owner
+            except (ImportError, RuntimeError):
+                wrapped = None
+        if wrapped is None:
+            wrapped = np.asarray(apply_pbc(positions), dtype=np.float64)
+        return wrapped
+
+    @property
+    def positions_ts(self) -> np.ndarray:
+        """(A copy of) the wrapped positions time series, shape (S,N,3)."""
+        if _is_torch_tensor(self._positions_ts):
+            return self._positions_ts.cpu().numpy()
+        return self._positions_ts.copy()
+
+    @property
+    def timestep(self) -> float:
+        return self._timestep
+
+    @property
+    def is_device_resident(self) -> bool:
+        return _is_torch_tensor(self._positions_ts)
+
+    def get_raman_spectrum(self, polarizability_model: PolarizabilityModel) -> MDRamanSpectrum:
+        """One ``calc_polarizabilities`` call over the whole trajectory, wrapped into an
+        ``MDRamanSpectrum`` (``_trajectory.py:71-90``).  With this package's models the
+        polarizability series stays on the GPU for ``measure``."""
+        try:
+            to_device = getattr(polarizability_model, "calc_polarizabilities_to_device", None)
+            if to_device is not None and not self.is_device_resident:
+                polarizability_ts = to_device(self._positions_ts)
+            else:
+                polarizability_ts = polarizability_model.calc_polarizabilities(self._positions_ts)
+        except ValueError as exc:
+            raise ValueError("polarizability_model and trajectory are incompatible") from exc
+        return MDRamanSpectrum(polarizability_ts, self._timestep)
+
+    def __len__(self) -> int:
+        return int(self._positions_ts.shape[0])
+
+    def __getitem__(self, key):
+        try:
+            item = self._positions_ts[key]
+        except IndexError as exc:
+            if "out of bounds" in str(exc) or "out of range" in str(exc):
+                raise IndexError("trajectory index out of bounds") from exc
+            raise exc
+        return item.cpu().numpy() if _is_torch_tensor(item) else item

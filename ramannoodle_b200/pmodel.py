@@ -1,0 +1,266 @@
+"""Drop-in evaluators for the reference's ``InterpolationModel`` / ``ARTModel``.
+
+The public method is the reference's plugin entry,
+``calc_polarizabilities(positions_batch) -> (S,3,3)`` (``ramannoodle/abstract.py:13-29``,
+``ramannoodle/pmodel/_interpolation.py:191-252``) with the same error behaviour.  The entry
+BASELINE.json's north_star names, ``get_polarizability(cart_displacements)``, is provided as
+well (it starts at ``_interpolation.py:233``).  Model *construction* stays in the
+reference: build the model there (``add_dof*``, ``add_art*``), then wrap it with
+``InterpolationModel.from_reference(model)`` (or ``ramannoodle_b200.accelerate(model)``).
+
+numpy in -> numpy out; a CUDA ``torch.Tensor`` in -> a CUDA tensor out (no host round trip).
+All arithmetic runs in the CUDA library; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .abstract import PolarizabilityModel
+from .exceptions import UserError, get_shape_error, get_type_error, verify_ndarray_shape
+from .state import ModelState
+
+
+def _is_torch_tensor(obj) -> bool:
+    return type(obj).__module__.startswith("torch") and hasattr(obj, "data_ptr")
+
+
+def _ptr(array: np.ndarray) -> ctypes.c_void_p:
+    return ctypes.c_void_p(array.ctypes.data)
+
+
+class _DeviceModel:
+    """Owns one ``rn_model`` handle (``include/ramannoodle_b200.h: rn_model_create``)."""
+
+    def __init__(self, state: ModelState, device: int, force_dense: bool) -> None:
+        tables = state.tables()
+        self.device = device
+        handle = ctypes.c_void_p()
+        flags = _lib.RN_MODEL_FORCE_DENSE if force_dense else _lib.RN_MODEL_DEFAULT
+        status = _lib.lib().rn_model_create(
+            _ptr(state.ref_positions), state.num_atoms, _ptr(state.lattice), _ptr(tables["basis"]),
+            state.num_dofs, _ptr(tables["degree"]), _ptr(tables["knot_off"]), _ptr(tables["knots"]),
+            _ptr(tables["coef_off"]), _ptr(tables["coefs"]), _ptr(tables["weight"]),
+            _ptr(state.ref_polarizability), device, flags, ctypes.byref(handle))
+        _lib.check(status, "rn_model_create")
+        self.handle = handle
+        info = (ctypes.c_int64 * 8)()
+        _lib.check(_lib.lib().rn_model_info(self.handle, info), "rn_model_info")
+        self.info = {"num_atoms": info[0], "num_dofs": info[1], "affine_dofs": info[2], "dense_dofs": info[3],
+                     "dense_degree": info[4], "device": info[5], "tma_affine": bool(info[6]),
+                     "dense_max_pieces": info[7]}
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            _lib.lib().rn_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+class InterpolationModel(PolarizabilityModel):
+    """GPU evaluator holding the state of a reference ``InterpolationModel``.
+
+    Parameters
+    ----------
+    state
+        The evaluation state (see ``ModelState``).
+    device
+        CUDA device index; defaults to torch's current device.
+    force_dense
+        Evaluate linear DOFs through the dense DMMA projection too (no affine collapse).
+    """
+
+    def __init__(self, state: ModelState, device: int | None = None, force_dense: bool = False) -> None:
+        self._state = state
+        self._device = device
+        self._force_dense = bool(force_dense)
+        self._native: _DeviceModel | None = None
+        self._native_key = None
+
+    # -- construction -------------------------------------------------------------------
+    @classmethod
+    def from_reference(cls, model, device: int | None = None, force_dense: bool = False):
+        """Wrap a model built with the reference package (state is snapshotted)."""
+        return cls(ModelState.from_reference(model), device=device, force_dense=force_dense)
+
+    # -- mirrored properties (``_interpolation.py:117-189``) ------------------------------
+    @property
+    def state(self) -> ModelState:
+        return self._state
+
+    @property
+    def num_atoms(self) -> int:
+        return self._state.num_atoms
+
+    @property
+    def ref_polarizability(self) -> np.ndarray:
+        return self._state.ref_polarizability.copy()
+
+    @property
+    def is_dummy_model(self) -> bool:
+        return self._state.is_dummy_model
+
+    @property
+    def cart_basis_vectors(self) -> list:
+        return copy.deepcopy(self._state.basis_vectors)
+
+    @property
+    def mask(self) -> np.ndarray:
+        return self._state.mask.copy()
+
+    @mask.setter
+    def mask(self, value) -> None:
+        verify_ndarray_shape("mask", value, self._state.mask.shape)
+        self._state.mask = np.asarray(value, dtype=bool)
+
+    def unmask(self) -> None:
+        """``_interpolation.py:710-712``."""
+        self._state.mask = np.zeros(self._state.mask.shape, dtype=bool)
+
+    def get_masked_model(self, dof_indexes_to_mask):
+        """``_interpolation.py:697-708``: a copy with the given DOFs masked."""
+        result = copy.deepcopy(self)
+        new_mask = result.mask
+        new_mask[:] = False
+        new_mask[dof_indexes_to_mask] = True
+        result.mask = new_mask
+        return result
+
+    def __deepcopy__(self, memo):
+        clone = type(self)(copy.deepcopy(self._state, memo), device=self._device, force_dense=self._force_dense)
+        return clone
+
+    def path_info(self) -> dict:
+        """Which kernels this model runs through (affine collapse / dense projection)."""
+        return dict(self._native_model().info)
+
+    # -- native handle --------------------------------------------------------------------
+    def _resolve_device(self, tensor=None) -> int:
+        if tensor is not None:
+            return int(tensor.device.index if tensor.device.index is not None else 0)
+        if self._device is not None:
+            return int(self._device)
+        try:
+            import torch  # pylint: disable=import-outside-toplevel
+
+            if torch.cuda.is_available():
+                return int(torch.cuda.current_device())
+        except ImportError:
+            pass
+        return 0
+
+    def _native_model(self, device: int | None = None) -> _DeviceModel:
+        if device is None:
+            device = self._resolve_device()
+        key = (device, self._state.fingerprint())
+        if self._native is None or self._native_key != key:
+            _lib.require_device(device)
+            if self._native is not None:
+                self._native.close()
+            self._native = _DeviceModel(self._state, device, self._force_dense)
+            self._native_key = key
+        return self._native
+
+    # -- evaluation -----------------------------------------------------------------------
+    def _check_dummy(self) -> None:
+        # zip(..., strict=True) over unequal lists raises ValueError in the reference, which a
+        # dummy model reports as UserError (_interpolation.py:245-250; test_art.py:367-369)
+        if len(self._state.splines) != len(self._state.basis_vectors):
+            if self._state.is_dummy_model:
+                raise UserError("dummy model cannot calculate polarizabilities")
+            raise ValueError("basis vectors and interpolations have different lengths")
+
+    def calc_polarizabilities(self, positions_batch):
+        """Return polarizabilities (S,3,3) for fractional positions (S,N,3)."""
+        if _is_torch_tensor(positions_batch):
+            return self._eval_tensor(positions_batch, wrap=True, name="positions", columns=None)
+        if not isinstance(positions_batch, np.ndarray):
+            raise get_type_error("positions", positions_batch, "ndarray")
+        if positions_batch.ndim != 3 or positions_batch.shape[1:] != (self.num_atoms, 3):
+            raise get_shape_error("positions", positions_batch, f"(_,{self.num_atoms},3)")
+        self._check_dummy()
+        positions = np.ascontiguousarray(positions_batch, dtype=np.float64)
+        num_frames = positions.shape[0]
+        alpha = np.empty((num_frames, 3, 3), dtype=np.float64)
+        native = self._native_model()
+        status = _lib.lib().rn_calc_polarizabilities_host(native.handle, _ptr(positions), num_frames, _ptr(alpha),
+                                                          None, 0)
+        _lib.check(status, "rn_calc_polarizabilities_host")
+        return alpha
+
+    def calc_polarizabilities_to_device(self, positions_batch: np.ndarray):
+        """Host positions in, polarizabilities left on the GPU (a CUDA tensor): the path
+        ``Trajectory.get_raman_spectrum`` uses so the series never round-trips to the host."""
+        import torch  # pylint: disable=import-outside-toplevel
+
+        if not isinstance(positions_batch, np.ndarray):
+            raise get_type_error("positions", positions_batch, "ndarray")
+        if positions_batch.ndim != 3 or positions_batch.shape[1:] != (self.num_atoms, 3):
+            raise get_shape_error("positions", positions_batch, f"(_,{self.num_atoms},3)")
+        self._check_dummy()
+        positions = np.ascontiguousarray(positions_batch, dtype=np.float64)
+        device = self._resolve_device()
+        native = self._native_model(device)
+        alpha = torch.empty((positions.shape[0], 3, 3), dtype=torch.float64, device=f"cuda:{device}")
+        torch.cuda.synchronize(device)
+        status = _lib.lib().rn_calc_polarizabilities_host(native.handle, _ptr(positions), positions.shape[0], None,
+                                                          ctypes.c_void_p(alpha.data_ptr()), 0)
+        _lib.check(status, "rn_calc_polarizabilities_host")
+        return alpha
+
+    def get_polarizability(self, cart_displacements):
+        """Polarizabilities from precomputed Cartesian displacements (S,N,3) or (S,3N) in Å
+        (what ``_interpolation.py:217-223`` produces)."""
+        if _is_torch_tensor(cart_displacements):
+            return self._eval_tensor(cart_displacements, wrap=False, name="cart_displacements", columns=None)
+        if not isinstance(cart_displacements, np.ndarray):
+            raise get_type_error("cart_displacements", cart_displacements, "ndarray")
+        import torch  # pylint: disable=import-outside-toplevel
+
+        device = self._resolve_device()
+        _lib.require_device(device)
+        tensor = torch.from_numpy(np.ascontiguousarray(cart_displacements, dtype=np.float64)).to(f"cuda:{device}")
+        return self._eval_tensor(tensor, wrap=False, name="cart_displacements", columns=None).cpu().numpy()
+
+    def _eval_tensor(self, tensor, wrap: bool, name: str, columns):
+        import torch  # pylint: disable=import-outside-toplevel
+
+        if not tensor.is_cuda:
+            raise get_type_error(name, tensor, "ndarray or CUDA tensor")
+        dim = 3 * self.num_atoms
+        ok = (tensor.ndim == 3 and tuple(tensor.shape[1:]) == (self.num_atoms, 3)) or (
+            not wrap and tensor.ndim == 2 and tensor.shape[1] == dim)
+        if not ok:
+            raise get_shape_error(name, tensor, f"(_,{self.num_atoms},3)")
+        self._check_dummy()
+        data = tensor.to(torch.float64).contiguous()
+        device = self._resolve_device(data)
+        native = self._native_model(device)
+        num_frames = int(data.shape[0])
+        with torch.cuda.device(device):
+            alpha = torch.empty((num_frames, 3, 3), dtype=torch.float64, device=data.device)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            entry = _lib.lib().rn_calc_polarizabilities if wrap else _lib.lib().rn_get_polarizability
+            status = entry(native.handle, ctypes.c_void_p(data.data_ptr()), num_frames,
+                           ctypes.c_void_p(alpha.data_ptr()), stream)
+        _lib.check(status, "rn_calc_polarizabilities" if wrap else "rn_get_polarizability")
+        return alpha
+
+
+class ARTModel(InterpolationModel):
+    """Atomic-Raman-tensor model (``ramannoodle/pmodel/_art.py:48``): evaluation is inherited
+    unchanged; every DOF is one linear piece, so it runs through the affine kernel."""
+
+
+def accelerate(model, device: int | None = None, force_dense: bool = False) -> InterpolationModel:
+    """Wrap a reference ``InterpolationModel``/``ARTModel`` for GPU evaluation."""
+    cls = ARTModel if type(model).__name__ == "ARTModel" else InterpolationModel
+    return cls.from_reference(model, device=device, force_dense=force_dense)

@@ -1,0 +1,214 @@
+"""Parity of the CUDA polarizability kernels (through the C-ABI) against the CPU oracle and
+the golden vectors generated from the unmodified reference.  Tolerance: max|new-ref| /
+max|ref| <= 1e-10 (BASELINE.json north_star)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import ramannoodle_b200 as rb
+from oracle import numpy_port as ora
+from oracle.make_golden import SYNTHETIC_CASES
+from ramannoodle_b200 import _lib, synthetic
+
+from gpu_helpers import ALPHA_RTOL, to_cuda
+from helpers import GOLDEN, oracle_model, rel_err, state_from_tables
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(model, positions, want, tol=ALPHA_RTOL):
+    got_host = model.calc_polarizabilities(positions)
+    assert got_host.shape == want.shape and got_host.dtype == np.float64
+    assert rel_err(got_host, want) <= tol
+    got_dev = model.calc_polarizabilities(to_cuda(positions))
+    assert got_dev.is_cuda
+    assert rel_err(got_dev.cpu().numpy(), want) <= tol
+    return got_host
+
+
+@pytest.mark.parametrize("prefix", ["k1", "k2", "k3", "art"])
+def test_real_tio2_golden(prefix):
+    """25 real DFT geometries (``test/tests/test_phonon_spectrum.py:33-45``) through the GPU."""
+    with np.load(f"{GOLDEN}/real_tio2.npz") as data:
+        state = state_from_tables(data, prefix)
+        model = rb.InterpolationModel(state)
+        got = _check(model, data["positions"], data[f"{prefix}_alpha"])
+        if prefix != "art":
+            assert np.allclose(got, data["known_polarizabilities"], atol=1e-4)
+        # S=1 batches, as Phonons.get_raman_spectrum issues them (dynamics/_phonon.py:96-101)
+        one = model.calc_polarizabilities(data["positions"][3:4])
+        assert rel_err(one, data[f"{prefix}_alpha"][3:4]) <= ALPHA_RTOL
+        if prefix == "art":
+            model.mask = data["art_masked_mask"]
+            _check(model, data["positions"], data["art_masked_alpha"])
+
+
+@pytest.mark.parametrize("case", SYNTHETIC_CASES, ids=[c[0] for c in SYNTHETIC_CASES])
+def test_synthetic_golden(case):
+    name, structure, kind, num_dofs, noisy, masked, frames, hops, art = case
+    state = synthetic.make_model(structure, kind, num_dofs=num_dofs, noisy_basis=noisy, masked_fraction=masked)
+    positions = synthetic.make_trajectory(structure, frames, timestep=1.0, seed=4242, lattice_hops=hops)
+    model = (rb.ARTModel if art else rb.InterpolationModel)(state)
+    with np.load(f"{GOLDEN}/synthetic_cases.npz") as data:
+        _check(model, positions, data[f"{name}_alpha"])
+    info = model.path_info()
+    if kind == "art":
+        assert info["affine_dofs"] == state.num_dofs and info["dense_dofs"] == 0
+    elif kind in ("cubic", "quadratic"):
+        assert info["dense_dofs"] == state.num_dofs
+
+
+@pytest.mark.parametrize("frames", [1, 7, 8, 9, 63, 129, 1000])
+@pytest.mark.parametrize("structure,kind", [("LLZO", "art"), ("TiO2", "art"), ("STO", "art"), ("STO", "cubic"),
+                                            ("LLZO", "mixed")])
+def test_against_oracle_ragged_sizes(structure, kind, frames):
+    """Tile tails (S not a multiple of 8 / 128), odd atom counts (STO: 135), mixed degrees."""
+    num_dofs = None if kind == "art" else 140
+    state = synthetic.make_model(structure, kind, num_dofs=num_dofs, masked_fraction=0.1, seed=7)
+    positions = synthetic.make_trajectory(structure, frames, seed=frames, lattice_hops=(frames % 2 == 1))
+    want = ora.calc_polarizabilities(oracle_model(state), positions)
+    _check(rb.InterpolationModel(state), positions, want)
+
+
+def test_affine_kernels_agree_and_force_dense():
+    """TMA affine kernel == generic affine kernel == dense DMMA path on an ARTModel."""
+    state = synthetic.make_model("LLZO", "art", masked_fraction=0.1)
+    positions = synthetic.make_trajectory("LLZO", 300, seed=11)
+    want = ora.calc_polarizabilities(oracle_model(state), positions)
+    d_pos = to_cuda(positions)
+    model = rb.ARTModel(state)
+    assert model.path_info()["tma_affine"]
+    tma = model.calc_polarizabilities(d_pos).cpu().numpy()
+    _lib.lib().rn_debug_force_generic_affine(1)
+    try:
+        generic = model.calc_polarizabilities(d_pos).cpu().numpy()
+    finally:
+        _lib.lib().rn_debug_force_generic_affine(0)
+    dense = rb.ARTModel(state, force_dense=True)
+    assert dense.path_info()["dense_dofs"] == state.num_dofs
+    forced = dense.calc_polarizabilities(d_pos).cpu().numpy()
+    for got in (tma, generic, forced):
+        assert rel_err(got, want) <= ALPHA_RTOL
+    # unaligned device pointer (view starting 8 bytes into an allocation) -> generic fallback
+    flat = torch.empty(d_pos.numel() + 1, dtype=torch.float64, device=d_pos.device)
+    flat[1:] = d_pos.reshape(-1)
+    shifted = flat[1:].view(d_pos.shape)
+    assert shifted.data_ptr() % 16 == 8
+    assert rel_err(model.calc_polarizabilities(shifted).cpu().numpy(), want) <= ALPHA_RTOL
+
+
+@pytest.mark.parametrize("structure,kind", [("LLZO", "art"), ("STO", "cubic"), ("TiO2", "mixed")])
+def test_get_polarizability_from_cart_displacements(structure, kind):
+    """The north_star entry ``get_polarizability(cart_displacements)`` (= _interpolation.py:233-252)."""
+    state = synthetic.make_model(structure, kind, num_dofs=None if kind == "art" else 90, seed=3)
+    positions = synthetic.make_trajectory(structure, 77, seed=5)
+    omodel = oracle_model(state)
+    cart = ora.calc_cart_displacements(omodel, positions)
+    want = ora.get_polarizability(omodel, cart)
+    model = rb.InterpolationModel(state)
+    got = model.get_polarizability(cart)
+    assert rel_err(got, want) <= ALPHA_RTOL
+    got3 = model.get_polarizability(to_cuda(cart.reshape(77, -1, 3))).cpu().numpy()
+    assert rel_err(got3, want) <= ALPHA_RTOL
+
+
+def test_minimum_image_edge_cases():
+    """Ties of the wrap (d % 1 == 0.5 stays +0.5), exact zeros, tiny negatives, far images."""
+    state = synthetic.make_model("TiO2", "mixed", num_dofs=60, seed=9)
+    state.ref_positions = np.round(state.ref_positions * 8) / 8  # exactly representable
+    base = np.broadcast_to(state.ref_positions, (12,) + state.ref_positions.shape).copy()
+    offsets = np.array([0.5, -0.5, 1.5, -1.5, 0.25, -0.25, 1.0, -1.0, 1e-20, -1e-20, 7.5, 0.0])
+    positions = base + offsets[:, None, None]
+    want = ora.calc_polarizabilities(oracle_model(state), positions)
+    got = rb.InterpolationModel(state).calc_polarizabilities(positions)
+    assert rel_err(got, want) <= ALPHA_RTOL
+    art = synthetic.make_model("TiO2", "art", seed=9)
+    art.ref_positions = state.ref_positions
+    want = ora.calc_polarizabilities(oracle_model(art), positions)
+    assert rel_err(rb.ARTModel(art).calc_polarizabilities(positions), want) <= ALPHA_RTOL
+
+
+def test_extrapolation_and_nan():
+    """Amplitudes far outside the knot range use the end polynomials; NaN in -> NaN out."""
+    state = synthetic.make_model("STO", "cubic", num_dofs=100, seed=21)
+    positions = synthetic.make_trajectory("STO", 16, seed=2, noise=0.3)  # amplitudes >> 0.2 Å
+    want = ora.calc_polarizabilities(oracle_model(state), positions)
+    model = rb.InterpolationModel(state)
+    assert rel_err(model.calc_polarizabilities(positions), want) <= ALPHA_RTOL
+    positions[3, 5, 1] = np.nan
+    got = model.calc_polarizabilities(positions)
+    assert np.isnan(got[3]).all() and np.isfinite(np.delete(got, 3, axis=0)).all()
+
+
+def test_empty_batch_and_no_dofs():
+    state = synthetic.make_model("TiO2", "art", num_dofs=10)
+    model = rb.ARTModel(state)
+    assert model.calc_polarizabilities(np.zeros((0, 108, 3))).shape == (0, 3, 3)
+    empty = rb.ModelState(state.ref_positions, state.lattice, state.ref_polarizability)
+    got = rb.InterpolationModel(empty).calc_polarizabilities(synthetic.make_trajectory("TiO2", 5))
+    assert np.array_equal(got, np.broadcast_to(state.ref_polarizability, (5, 3, 3)))
+
+
+def test_mask_mutation_and_deepcopy():
+    """Models are mutable (mask setter, unmask) and deep-copied by get_masked_model
+    (_interpolation.py:174-189,697-712): the device tables must follow."""
+    state = synthetic.make_model("LLZO", "mixed", num_dofs=50, seed=4)
+    positions = synthetic.make_trajectory("LLZO", 20, seed=8)
+    model = rb.InterpolationModel(state)
+    omodel = oracle_model(state)
+    assert rel_err(model.calc_polarizabilities(positions), ora.calc_polarizabilities(omodel, positions)) <= ALPHA_RTOL
+    masked = model.get_masked_model([0, 3, 17])
+    omasked = copy.deepcopy(omodel)
+    omasked.mask = masked.mask
+    assert rel_err(masked.calc_polarizabilities(positions), ora.calc_polarizabilities(omasked, positions)) <= ALPHA_RTOL
+    assert not model.mask.any()
+    mask = model.mask
+    mask[5] = True
+    model.mask = mask
+    omodel.mask = mask
+    assert rel_err(model.calc_polarizabilities(positions), ora.calc_polarizabilities(omodel, positions)) <= ALPHA_RTOL
+    model.unmask()
+    omodel.mask = np.zeros(50, dtype=bool)
+    assert rel_err(model.calc_polarizabilities(positions), ora.calc_polarizabilities(omodel, positions)) <= ALPHA_RTOL
+
+
+def test_error_behaviour():
+    """Messages pinned by the reference's tests."""
+    state = synthetic.make_model("TiO2", "art", num_dofs=6)
+    model = rb.ARTModel(state)
+    with pytest.raises(TypeError, match="positions should have type ndarray, not list"):
+        model.calc_polarizabilities([[1.0, 2.0, 3.0]])
+    with pytest.raises(ValueError, match=r"positions has wrong shape: \(4,5,3\) != \(_,108,3\)"):
+        model.calc_polarizabilities(np.zeros((4, 5, 3)))
+    with pytest.raises(ValueError, match=r"positions has wrong shape: \(108,3\) != \(_,108,3\)"):
+        model.calc_polarizabilities(np.zeros((108, 3)))
+    dummy = rb.ModelState(state.ref_positions, state.lattice, np.zeros((3, 3)), is_dummy_model=True)
+    dummy.basis_vectors.append(np.zeros((108, 3)))
+    dummy.mask = np.array([False])
+    with pytest.raises(rb.UserError, match="dummy model cannot calculate polarizabilities"):
+        rb.ARTModel(dummy).calc_polarizabilities(np.zeros((1, 108, 3)))
+
+
+def test_large_batch_linearity_property():
+    """Full-size property check (no oracle at this size): for an ARTModel alpha - alpha0 is
+    linear in the wrapped displacement, so alpha(p_ref + 2d) - alpha0 == 2 (alpha(p_ref + d) - alpha0)."""
+    state = synthetic.make_model("LLZO", "art")
+    model = rb.ARTModel(state)
+    frames = 200_000
+    pos = synthetic.make_trajectory_cuda("LLZO", frames, "cuda:0", seed=123, noise=0.01)
+    ref = to_cuda(state.ref_positions)
+    disp = pos - ref
+    disp = disp - torch.round(disp)
+    a1 = model.calc_polarizabilities(ref + disp)
+    a2 = model.calc_polarizabilities(ref + 2 * disp)
+    a0 = model.calc_polarizabilities(ref[None])
+    lhs = (a2 - a0).cpu().numpy()
+    rhs = 2 * (a1 - a0).cpu().numpy()
+    assert rel_err(lhs, rhs) <= 1e-10
+    # and the first / last frames against the oracle
+    sel = np.r_[0:64, frames - 64:frames]
+    want = ora.calc_polarizabilities(oracle_model(state), pos[sel].cpu().numpy())
+    got = model.calc_polarizabilities(pos)[sel].cpu().numpy()
+    assert rel_err(got, want) <= ALPHA_RTOL

@@ -1,0 +1,148 @@
+"""Parity of the CUDA spectrum path (Bluestein FFT, orientational average, corrections,
+smearing) against the oracle and the reference-generated goldens.
+Tolerance: pointwise relative error <= 1e-8 on intensities (BASELINE.json north_star);
+wavenumbers are reproduced bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+import ramannoodle_b200 as rb
+from oracle import numpy_port as ora
+
+from gpu_helpers import INTENSITY_RTOL, to_cuda
+from helpers import GOLDEN, pointwise_rel_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("frames", [41, 52, 258, 1000, 4097])
+def test_measure_golden(frames):
+    key = f"s{frames}"
+    with np.load(f"{GOLDEN}/spectrum_cases.npz") as data:
+        alpha, dt = data[f"{key}_alpha"], float(data[f"{key}_timestep"])
+        spectrum = rb.MDRamanSpectrum(alpha, dt)
+        wn, inten = spectrum.measure()
+        assert np.array_equal(wn, data[f"{key}_raw_wavenumbers"])
+        assert pointwise_rel_err(inten, data[f"{key}_raw_intensities"]) <= INTENSITY_RTOL
+        wn, inten = spectrum.measure(laser_correction=True, laser_wavelength=532,
+                                     bose_einstein_correction=True, temperature=300)
+        assert np.array_equal(wn, data[f"{key}_corr_wavenumbers"])
+        assert pointwise_rel_err(inten, data[f"{key}_corr_intensities"]) <= INTENSITY_RTOL
+        # device-resident series (what Trajectory.get_raman_spectrum hands over)
+        wn2, inten2 = rb.MDRamanSpectrum(to_cuda(alpha), dt).measure()
+        assert np.array_equal(wn2, data[f"{key}_raw_wavenumbers"])
+        assert pointwise_rel_err(inten2, data[f"{key}_raw_intensities"]) <= INTENSITY_RTOL
+
+
+@pytest.mark.parametrize("length", [1, 2, 3, 4, 5, 7, 8, 16, 17, 40, 51, 64, 127, 128, 129, 257, 1021, 4096, 9999])
+def test_signal_spectrum_vs_oracle(length):
+    """calc_signal_spectrum for powers of two, primes and composites (test_trajectory_spectrum.py:18-32
+    pins the ceil(S/2) output length)."""
+    signal = np.random.default_rng(length).normal(size=length)
+    wn, inten = rb.calc_signal_spectrum(signal, 1.5)
+    ref_wn, ref_inten = ora.calc_signal_spectrum(signal, 1.5)
+    assert wn.shape == (int(np.ceil(length / 2)),) and inten.shape == wn.shape
+    assert np.array_equal(wn, ref_wn)
+    # I[k] >= sum(x^2)/2 > 0, so pointwise relative error is well conditioned
+    assert pointwise_rel_err(inten, ref_inten) <= INTENSITY_RTOL
+
+
+def test_measure_large_series_vs_oracle():
+    """S = 200001 (M = 2^6 * 5^5, Bluestein length 2^19) against the scipy-based oracle."""
+    rng = np.random.default_rng(5)
+    frames = 200_001
+    steps = np.arange(frames)[:, None, None]
+    alpha = (6.0 * np.eye(3)[None] + 0.05 * np.sin(0.013 * steps + rng.uniform(0, 6, (1, 3, 3)))
+             + 0.01 * rng.normal(size=(frames, 3, 3)))
+    wn, inten = rb.MDRamanSpectrum(alpha, 1.0).measure(laser_correction=True, bose_einstein_correction=True)
+    ref_wn, ref_inten = ora.md_measure(alpha, 1.0, laser_correction=True, bose_einstein_correction=True)
+    assert np.array_equal(wn, ref_wn)
+    assert pointwise_rel_err(inten, ref_inten) <= INTENSITY_RTOL
+
+
+def test_parseval_property_full_size():
+    """Size-independent check at S = 1e6+1 (no CPU oracle needed): for a real signal
+    sum_k |X_k|^2 = M sum_n x_n^2, hence sum over ALL M bins of I = (|X|^2+E)/2 is M*E.
+    With the first ceil(M/2) bins returned and Hermitian symmetry this pins the FFT scale."""
+    M = 1_000_000
+    x = torch.randn(M, dtype=torch.float64, device="cuda:0", generator=torch.Generator("cuda:0").manual_seed(3))
+    wn, inten = rb.calc_signal_spectrum(x.cpu().numpy(), 1.0)
+    energy = float((x * x).sum())
+    # bins 1..M/2-1 appear twice in the full spectrum, bins 0 and M/2 once
+    xf = torch.fft.fft(x)
+    p_half = float((xf[M // 2].abs() ** 2 + energy) / 2)
+    total = inten[0] + 2 * inten[1:].sum() + p_half
+    assert abs(total - M * energy) / (M * energy) < 1e-10
+    ref = ((xf[: M // 2].abs() ** 2 + energy) / 2).cpu().numpy()  # independent FFT (cuFFT via torch) as a cross-check
+    assert pointwise_rel_err(inten, ref) <= INTENSITY_RTOL
+
+
+@pytest.mark.parametrize("function", ["gaussian", "lorentzian"])
+def test_reference_smearing_goldens(function):
+    """The reference's own goldens (test/tests/test_phonon_spectrum.py:403-449)."""
+    with np.load(f"{GOLDEN}/smearing.npz") as data:
+        wn, inten = data["known_spectrum_wavenumbers"], data["known_spectrum_intensities"]
+        cw, ci = rb.convolve_spectrum(wn, inten, function)
+        assert np.allclose(cw, data[f"known_{function}_spectrum_wavenumbers"])
+        assert np.allclose(ci, data[f"known_{function}_spectrum_intensities"])
+        ow, oi = ora.convolve_spectrum(wn, inten, function)
+        assert np.array_equal(cw, ow)
+        assert rel_err(ci, oi) <= 1e-12
+
+
+def test_smearing_md_golden_and_custom_grid():
+    with np.load(f"{GOLDEN}/spectrum_cases.npz") as data:
+        wn, inten = data["s1000_corr_wavenumbers"], data["s1000_corr_intensities"]
+        for function in ("gaussian", "lorentzian"):
+            cw, ci = rb.convolve_spectrum(wn, inten, function, 7.5)
+            assert np.array_equal(cw, data[f"s1000_{function}_wavenumbers"])
+            assert rel_err(ci, data[f"s1000_{function}_intensities"]) <= 1e-12
+        grid = np.linspace(-50.0, 900.0, 333)
+        cw, ci = rb.convolve_spectrum(wn, inten, "gaussian", 3.0, grid)
+        assert cw is grid
+        assert rel_err(ci, data["s1000_grid_intensities"]) <= 1e-12
+
+
+def test_smearing_many_points_with_tile_skipping():
+    """Enough input points that far-apart (input chunk, output tile) pairs are skipped: the
+    skipped Gaussian factors underflow to exactly 0, so the result still matches."""
+    rng = np.random.default_rng(8)
+    wn = np.sort(rng.uniform(1.0, 4000.0, 30_000))
+    inten = rng.uniform(0.0, 2.0, 30_000)
+    grid = np.linspace(-100.0, 4100.0, 1500)
+    for function, width in (("gaussian", 2.0), ("lorentzian", 6.0)):
+        _, got = rb.convolve_spectrum(wn, inten, function, width, grid)
+        _, want = ora.convolve_spectrum(wn[:3000], inten[:3000], function, width, grid)
+        _, got_small = rb.convolve_spectrum(wn[:3000], inten[:3000], function, width, grid)
+        assert rel_err(got_small, want) <= 1e-12
+        # full-size: compare against a float64 torch evaluation of the same sum
+        d_wn, d_in, d_grid = to_cuda(wn), to_cuda(inten), to_cuda(grid)
+        dx = d_wn[None, :] - d_grid[:, None]
+        if function == "gaussian":
+            factor = (1 / width) * (1 / np.sqrt(2 * np.pi)) * torch.exp(-(dx**2) / (2 * width**2))
+        else:
+            factor = (1 / np.pi) * (0.5 * width / (dx**2 + (0.5 * width) ** 2))
+        ref = (factor * d_in[None, :]).sum(dim=1).cpu().numpy()
+        assert rel_err(got, ref) <= 1e-12
+
+
+def test_spectrum_error_behaviour():
+    alpha = np.random.default_rng(0).normal(size=(30, 3, 3))
+    spectrum = rb.MDRamanSpectrum(alpha, 1.0)
+    with pytest.raises(NotImplementedError, match="only polycrystalline spectra are supported for now"):
+        spectrum.measure(orientation="single crystal")
+    with pytest.raises(ValueError, match="invalid temperature: -1 <= 0"):
+        spectrum.measure(bose_einstein_correction=True, temperature=-1)
+    with pytest.raises(ValueError, match="invalid laser_wavenumber"):
+        spectrum.measure(laser_correction=True, laser_wavelength=-5)
+    with pytest.raises(ValueError, match=r"polarizability_ts has wrong shape: \(30,3\) != \(_,3,3\)"):
+        rb.MDRamanSpectrum(alpha[:, 0], 1.0)
+    wn, inten = spectrum.measure()
+    with pytest.raises(ValueError, match="invalid width: -1 <= 0"):
+        rb.convolve_spectrum(wn, inten, "gaussian", -1)
+    with pytest.raises(ValueError, match="unsupported convolution type: blah"):
+        rb.convolve_spectrum(wn, inten, "blah", 3)
+    with pytest.raises(TypeError, match="intensities should have type ndarray, not list"):
+        rb.convolve_spectrum(np.array([1.0, 2.0, 3.0]), [0, 3, 0], "gaussian", 5)
+    with pytest.raises(ValueError, match=r"intensities has wrong shape: \(2,\) != \(3,\)"):
+        rb.convolve_spectrum(np.array([1.0, 2.0, 3.0]), np.array([0.0, 3.0]), "gaussian", 5)

@@ -81,16 +81,12 @@ __global__ void __launch_bounds__(256) affine_generic_kernel(const double* __res
 // ------------------------------------------------------------------------------------
 // TMA affine kernel
 // ------------------------------------------------------------------------------------
-constexpr int kStages = 4;
 constexpr int kRedStride = 12;  // doubles per (warp, frame) slot in the cross-warp reduction buffer
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -114,7 +110,7 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                  : "memory");
 }
 
-// Stage layout: 8 frame rows, each one bulk copy of K doubles, at a stride == 8 (mod 16)
+// Stage layout: 8*MT frame rows, each one bulk copy of K doubles, at a stride == 8 (mod 16)
 // doubles so that the LDS.128 fragment loads of two consecutive rows hit disjoint banks.
 // Requires K even (frame rows are then multiples of 16 bytes, as cp.async.bulk needs).
 struct AffineSmemLayout {
@@ -123,141 +119,198 @@ struct AffineSmemLayout {
     size_t bytes;
 };
 
-static AffineSmemLayout affine_layout(int K, int kp) {
+static AffineSmemLayout affine_layout(int K, int kp, int mt, int stages) {
     AffineSmemLayout L;
     L.row_stride = K + (8 - K % 16 + 16) % 16;
     const int slack = kAffineWarps * 8 * kp;  // fragment loads may run past the last row (values are masked)
-    L.stage_doubles = 8 * L.row_stride;
-    L.bytes = (size_t)(kStages * L.stage_doubles + slack) * 8 + (size_t)2 * kAffineWarps * 8 * kRedStride * 8 +
-              2 * kStages * 8 + 64;
+    L.stage_doubles = 8 * mt * L.row_stride;
+    L.bytes = (size_t)(stages * L.stage_doubles + slack) * 8 + (size_t)2 * kAffineWarps * 8 * mt * kRedStride * 8 +
+              (size_t)2 * slack * 8 + (size_t)stages * 8 + 64;
     return L;
 }
 
-template <int KP, bool WRAP>
-__global__ void __launch_bounds__((kAffineWarps + 1) * 32, 1)
+// 8 warps per CTA, two CTAs per SM when registers allow (while one CTA sits in its reduction /
+// barrier phase the other one computes).  A tile is 8*MT consecutive frames; STAGES bulk-copy
+// tiles are kept in flight per CTA.  Every warp contracts its own K-slice (8*KP elements) of all
+// rows of the tile: the DMMA B fragments (8 tensor components) stay in registers, the 9th
+// component's column of G and the reference positions are read from smem tables; partial 3x3
+// tensors are combined through smem.
+template <int KP, int MT, int STAGES, bool WRAP>
+__global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 1)
     affine_tma_kernel(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ G,
                       int64_t num_frames, int K, int row_stride, int stage_doubles, Alpha0 a0,
                       double* __restrict__ alpha) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int ROWS = 8 * MT;
+    constexpr int RED = kAffineWarps * ROWS * kRedStride;  // doubles per reduction buffer
     double* stages = reinterpret_cast<double*>(smem_raw);
     const int slack = kAffineWarps * 8 * KP;
-    double* red = stages + kStages * stage_doubles + slack;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2 * kAffineWarps * 8 * kRedStride);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages);
+    double* red = stages + STAGES * stage_doubles + slack;
+    double* tab_ref = red + 2 * RED;       // [kAffineWarps*8*KP] wrapped reference positions
+    double* tab_g9 = tab_ref + slack;      // [kAffineWarps*8*KP] column 8 of G
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tab_g9 + slack);
+    const uint32_t full0 = smem_u32(bars);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t num_tiles = (num_frames + 7) / 8;
+    const int64_t num_tiles = (num_frames + ROWS - 1) / ROWS;
+    const uint32_t row_bytes = (uint32_t)K * 8u;
+
+    auto issue_tile = [&](int64_t tile, int s) {
+        const int64_t frame0 = tile * ROWS;
+        const int rows = (int)min((int64_t)ROWS, num_frames - frame0);
+        mbar_arrive_expect_tx(full0 + 8 * s, row_bytes * rows);
+        const uint32_t dst0 = smem_u32(stages + (size_t)s * stage_doubles);
+        const double* src0 = in + frame0 * (int64_t)K;
+        for (int r = 0; r < rows; r++)
+            tma_bulk_g2s(dst0 + (uint32_t)(r * row_stride) * 8u, src0 + (int64_t)r * K, row_bytes, full0 + 8 * s);
+    };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, kAffineWarps);
-        }
+        for (int s = 0; s < STAGES; s++) mbar_init(full0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
+        for (int s = 0; s < STAGES; s++) {
+            const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
+            if (tile < num_tiles) issue_tile(tile, s);
+        }
+    }
+    for (int e = threadIdx.x; e < slack; e += blockDim.x) {  // tables are zero-padded to `slack` rows
+        tab_ref[e] = WRAP ? __ldg(ref + e) : 0.0;
+        tab_g9[e] = __ldg(G + (int64_t)e * 9 + 8);
     }
     __syncthreads();
 
-    if (warp == kAffineWarps) {
-        // ---------------- producer: one lane issues the bulk copies ----------------
-        if (lane == 0) {
-            int64_t i = 0;
-            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
-                const int s = (int)(i % kStages);
-                const uint32_t round = (uint32_t)(i / kStages);
-                if (round > 0) mbar_wait(empty0 + 8 * s, (round - 1) & 1);
-                const int64_t frame0 = tile * 8;
-                const int rows = (int)min((int64_t)8, num_frames - frame0);
-                const uint32_t row_bytes = (uint32_t)K * 8u;
-                mbar_arrive_expect_tx(full0 + 8 * s, row_bytes * rows);
-                const uint32_t dst0 = smem_u32(stages + (size_t)s * stage_doubles);
-                const double* src0 = in + frame0 * (int64_t)K;
-                for (int r = 0; r < rows; r++)
-                    tma_bulk_g2s(dst0 + (uint32_t)(r * row_stride) * 8u, src0 + (int64_t)r * K, row_bytes,
-                                 full0 + 8 * s);
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumers ----------------
     const int g = lane >> 2, t = lane & 3;
     const int kbase = warp * 8 * KP + 2 * t;
-    double refv[KP][2], b8[KP][2], b9[KP][2];
+    double b8[KP][2];
     uint32_t validmask = 0;
 #pragma unroll
     for (int p = 0; p < KP; p++) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const int e = kbase + 8 * p + h;  // tables are zero-padded to kAffineWarps*8*KP rows
-            refv[p][h] = WRAP ? __ldg(ref + e) : 0.0;
+            const int e = kbase + 8 * p + h;
             b8[p][h] = __ldg(G + (int64_t)e * 9 + g);
-            b9[p][h] = __ldg(G + (int64_t)e * 9 + 8);
             if (e < K) validmask |= 1u << (2 * p + h);
         }
     }
+    const double* my_ref = tab_ref + kbase;
+    const double* my_g9 = tab_g9 + kbase;
     const int rowoff = g * row_stride + kbase;
-    double* myred = red + ((size_t)warp * 8 + g) * kRedStride;
+    double* myred = red + ((size_t)warp * ROWS + g) * kRedStride;
 
     int64_t i = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
-        const int s = (int)(i % kStages);
-        mbar_wait(full0 + 8 * s, (uint32_t)(i / kStages) & 1);
+        const int s = (int)(i % STAGES);
+        mbar_wait(full0 + 8 * s, (uint32_t)(i / STAGES) & 1);
         const double* base = stages + (size_t)s * stage_doubles + rowoff;
-        double c0 = 0, c1 = 0, a9 = 0;
+        // independent accumulator chains (2 per 8-frame group): one DMMA/DFMA dependency chain
+        // per warp cannot cover the FP64 pipe latency with two warps per scheduler
+        double c0[MT][2], c1[MT][2], a9[MT][2];
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) c0[m][h] = c1[m][h] = a9[m][h] = 0.0;
 #pragma unroll
         for (int p = 0; p < KP; p++) {
-            const double2 v = *reinterpret_cast<const double2*>(base + 8 * p);
-            double a_lo = v.x, a_hi = v.y;
-            if (WRAP) {
-                a_lo = wrap_disp(a_lo, refv[p][0]);
-                a_hi = wrap_disp(a_hi, refv[p][1]);
+            const double2 g9 = *reinterpret_cast<const double2*>(my_g9 + 8 * p);
+            double2 rf = make_double2(0.0, 0.0);
+            if (WRAP) rf = *reinterpret_cast<const double2*>(my_ref + 8 * p);
+#pragma unroll
+            for (int m = 0; m < MT; m++) {
+                const double2 v = *reinterpret_cast<const double2*>(base + (size_t)m * 8 * row_stride + 8 * p);
+                double a_lo = v.x, a_hi = v.y;
+                if (WRAP) {
+                    a_lo = wrap_disp(a_lo, rf.x);
+                    a_hi = wrap_disp(a_hi, rf.y);
+                }
+                a_lo = (validmask >> (2 * p)) & 1u ? a_lo : 0.0;
+                a_hi = (validmask >> (2 * p + 1)) & 1u ? a_hi : 0.0;
+                dmma884(c0[m][0], c1[m][0], a_lo, b8[p][0]);
+                a9[m][0] = fma(a_lo, g9.x, a9[m][0]);
+                dmma884(c0[m][1], c1[m][1], a_hi, b8[p][1]);
+                a9[m][1] = fma(a_hi, g9.y, a9[m][1]);
             }
-            a_lo = (validmask >> (2 * p)) & 1u ? a_lo : 0.0;
-            a_hi = (validmask >> (2 * p + 1)) & 1u ? a_hi : 0.0;
-            dmma884(c0, c1, a_lo, b8[p][0]);
-            a9 = fma(a_lo, b9[p][0], a9);
-            dmma884(c0, c1, a_hi, b8[p][1]);
-            a9 = fma(a_hi, b9[p][1], a9);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * s);  // stage may be refilled
-        a9 += __shfl_xor_sync(0xffffffffu, a9, 1);
-        a9 += __shfl_xor_sync(0xffffffffu, a9, 2);
-        double* slot = myred + (size_t)(i & 1) * kAffineWarps * 8 * kRedStride;
-        *reinterpret_cast<double2*>(slot + 2 * t) = make_double2(c0, c1);
-        if (t == 0) slot[8] = a9;
-        asm volatile("bar.sync 1, %0;" ::"n"(kAffineWarps * 32) : "memory");
-        if (threadIdx.x < 72) {
+        double* slot = myred + (size_t)(i & 1) * RED;
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+            double a9s = a9[m][0] + a9[m][1];
+            a9s += __shfl_xor_sync(0xffffffffu, a9s, 1);
+            a9s += __shfl_xor_sync(0xffffffffu, a9s, 2);
+            *reinterpret_cast<double2*>(slot + (size_t)m * 8 * kRedStride + 2 * t) =
+                make_double2(c0[m][0] + c0[m][1], c1[m][0] + c1[m][1]);
+            if (t == 0) slot[(size_t)m * 8 * kRedStride + 8] = a9s;
+        }
+        __syncthreads();  // partials visible; every warp is done reading stage s
+        {
+            // refill stage s: thread 0 arms the barrier, lane 0 of warp w copies rows w, w+8, ...
+            const int64_t next = tile + (int64_t)STAGES * gridDim.x;
+            if (next < num_tiles && lane == 0) {
+                const int64_t frame0 = next * ROWS;
+                const int rows = (int)min((int64_t)ROWS, num_frames - frame0);
+                if (warp == 0) mbar_arrive_expect_tx(full0 + 8 * s, row_bytes * rows);
+                const uint32_t dst0 = smem_u32(stages + (size_t)s * stage_doubles);
+                const double* src0 = in + frame0 * (int64_t)K;
+                for (int r = warp; r < rows; r += kAffineWarps)
+                    tma_bulk_g2s(dst0 + (uint32_t)(r * row_stride) * 8u, src0 + (int64_t)r * K, row_bytes,
+                                 full0 + 8 * s);
+            }
+        }
+        if (threadIdx.x < 9 * ROWS) {
             const int f = threadIdx.x / 9, q = threadIdx.x % 9;
-            const double* r = red + (size_t)(i & 1) * kAffineWarps * 8 * kRedStride + (size_t)f * kRedStride + q;
+            const double* r = red + (size_t)(i & 1) * RED + (size_t)f * kRedStride + q;
             double sum = 0;
 #pragma unroll
-            for (int w = 0; w < kAffineWarps; w++) sum += r[(size_t)w * 8 * kRedStride];
-            const int64_t frame = tile * 8 + f;
+            for (int w = 0; w < kAffineWarps; w++) sum += r[(size_t)w * ROWS * kRedStride];
+            const int64_t frame = tile * ROWS + f;
             if (frame < num_frames) alpha[frame * 9 + q] = sum + a0.v[q];
         }
     }
 }
 
+static int g_affine_mt = 0;  // 0 = automatic
+
+template <int KP, int MT, int STAGES, bool WRAP>
+static int launch_affine_tma_cfg(const rn_model* m, const double* d_in, int64_t frames, double* d_alpha, Alpha0 a0,
+                                 cudaStream_t stream) {
+    const int K = (int)m->dim;
+    const AffineSmemLayout L = affine_layout(K, KP, MT, STAGES);
+    if (L.bytes > 227 * 1024) return 1;  // does not fit: caller tries a smaller configuration
+    const int64_t tiles = (frames + 8 * MT - 1) / (8 * MT);
+    const double* ref = WRAP ? m->d_ref_wrapped : m->d_zero_ref;
+    const double* G = WRAP ? m->d_g_frac : m->d_g_cart;
+    auto kern = affine_tma_kernel<KP, MT, STAGES, WRAP>;
+    RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+    int ctas_per_sm = 1;
+    RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kAffineWarps * 32, L.bytes));
+    if (ctas_per_sm < 1) return 1;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)m->sm_count * ctas_per_sm);
+    kern<<<grid, kAffineWarps * 32, L.bytes, stream>>>(d_in, ref, G, frames, K, L.row_stride, L.stage_doubles, a0,
+                                                       d_alpha);
+    RN_LAUNCHED();
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}
+
+template <int KP, bool WRAP>
+static int launch_affine_tma_kp(const rn_model* m, const double* d_in, int64_t frames, double* d_alpha, Alpha0 a0,
+                                cudaStream_t stream) {
+    // Measured on B200 (tools/tune_affine.py, 1M frames): LLZO (KP=9) 16-frame tiles, 1 CTA/SM:
+    // 6284 GB/s; 8-frame tiles, 2 CTAs/SM: 6200 GB/s.  TiO2 (KP=6): 4855 vs 5127 GB/s.
+    int mt = g_affine_mt;
+    if (mt == 0) mt = (KP >= 8) ? 2 : 1;
+    int rc = 1;
+    if (mt == 2) rc = launch_affine_tma_cfg<KP, 2, 2, WRAP>(m, d_in, frames, d_alpha, a0, stream);
+    if (rc == 1) rc = launch_affine_tma_cfg<KP, 1, 2, WRAP>(m, d_in, frames, d_alpha, a0, stream);
+    return rc;
+}
+
 template <bool WRAP>
 static int launch_affine_tma(const rn_model* m, const double* d_in, int64_t frames, double* d_alpha, Alpha0 a0,
                              cudaStream_t stream) {
-    const int K = (int)m->dim;
-    const AffineSmemLayout L = affine_layout(K, m->affine_kp);
-    const int64_t tiles = (frames + 7) / 8;
-    const int grid = (int)std::min<int64_t>(tiles, m->sm_count);
-    const double* ref = WRAP ? m->d_ref_wrapped : m->d_zero_ref;
-    const double* G = WRAP ? m->d_g_frac : m->d_g_cart;
-#define RN_AFFINE_CASE(KP)                                                                                     \
-    case KP: {                                                                                                 \
-        auto kern = affine_tma_kernel<KP, WRAP>;                                                               \
-        RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));        \
-        kern<<<grid, (kAffineWarps + 1) * 32, L.bytes, stream>>>(d_in, ref, G, frames, K, L.row_stride,         \
-                                                                 L.stage_doubles, a0, d_alpha);                \
-        break;                                                                                                 \
-    }
     switch (m->affine_kp) {
+#define RN_AFFINE_CASE(KP) \
+    case KP: return launch_affine_tma_kp<KP, WRAP>(m, d_in, frames, d_alpha, a0, stream);
         RN_AFFINE_CASE(1)
         RN_AFFINE_CASE(2)
         RN_AFFINE_CASE(3)
@@ -270,14 +323,11 @@ static int launch_affine_tma(const rn_model* m, const double* d_in, int64_t fram
         RN_AFFINE_CASE(10)
         RN_AFFINE_CASE(11)
         RN_AFFINE_CASE(12)
+#undef RN_AFFINE_CASE
         default:
             set_error("affine TMA kernel not compiled for KP=%d", m->affine_kp);
             return RN_ERR_UNSUPPORTED;
     }
-#undef RN_AFFINE_CASE
-    RN_LAUNCHED();
-    RN_CUDA(cudaGetLastError());
-    return RN_OK;
 }
 
 template <bool WRAP>
@@ -305,13 +355,15 @@ int launch_affine(const rn_model* m, const double* d_in, bool wrap, int64_t num_
     int64_t tma_frames = 0;
     if (m->affine_kp > 0 && aligned && !g_force_generic_affine) {
         tma_frames = num_frames;
-        const AffineSmemLayout L = affine_layout(K, m->affine_kp);
-        if (L.bytes > 227 * 1024) tma_frames = 0;
     }
     int rc = RN_OK;
     if (tma_frames > 0) {
         rc = wrap ? launch_affine_tma<true>(m, d_in, tma_frames, d_alpha, a0, stream)
                   : launch_affine_tma<false>(m, d_in, tma_frames, d_alpha, a0, stream);
+        if (rc == 1) {  // no configuration fits in shared memory
+            tma_frames = 0;
+            rc = RN_OK;
+        }
         if (rc != RN_OK) return rc;
     }
     if (tma_frames < num_frames) {
@@ -605,6 +657,11 @@ extern "C" int rn_get_polarizability(const rn_model* model, const double* d_cart
 
 // Test hook (not in the public header): route the affine term through the generic kernel.
 extern "C" void rn_debug_force_generic_affine(int on) { rn::g_force_generic_affine = on != 0; }
+// Tuning hook: frames-per-tile multiplier (1 or 2) and pipeline depth of the TMA affine kernel.
+extern "C" void rn_debug_set_affine_config(int mt, int stages) {
+    (void)stages;
+    rn::g_affine_mt = mt;
+}
 
 __global__ void apply_pbc_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t count) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {

@@ -11,6 +11,7 @@
 // three complex sequences; the invariant combinations (trace, xx-yy, ...) are formed in the
 // frequency domain (FFT linearity), their energies in the time domain.
 #include <cmath>
+#include <type_traits>
 
 #include "rn_common.cuh"
 
@@ -18,16 +19,25 @@ struct rn_spectrum_plan {
     int device = 0;
     int sm_count = 0;
     int64_t S = 0, M = 0, L = 0;
+    int log2l = 0;
+    int num_passes = 0;
+    int pass_log2r[4] = {0, 0, 0, 0};
+    int split = 0;                // two-level twiddle split: m = hi << split | lo
     double2* d_buf0 = nullptr;    // L
     double2* d_buf1 = nullptr;    // L
     double2* d_filter = nullptr;  // L   FFT of the chirp filter
     double2* d_spec = nullptr;    // 3*M  chirp-z outputs (unscaled by 1/L)
+    double2* d_chirp = nullptr;   // M   exp(-i pi n^2 / M)
+    double2* d_whi = nullptr;     // L >> split   exp(-2 pi i (a << split) / L)
+    double2* d_wlo = nullptr;     // 1 << split   exp(-2 pi i b / L)
+    double2* d_wsub = nullptr;    // 4096         exp(-2 pi i m / 4096)
     double* d_partial = nullptr;  // energy_blocks * 8
     double* d_energy = nullptr;   // 8
     int energy_blocks = 0;
 };
 
 namespace rn {
+
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -87,126 +97,301 @@ __device__ __forceinline__ void dft8(double2* v) {
     v[7] = csub(e[3], o3);
 }
 
-// One Stockham radix-R pass over a length-L sequence; Ns = product of the radices already done.
-// SGN = -1 forward, +1 inverse (unscaled).  MULH multiplies the input by H (pointwise) first.
-template <int R, int SGN, bool MULH>
-__global__ void __launch_bounds__(256) fft_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
-                                                       const double2* __restrict__ H, int64_t L, int64_t Ns) {
-    const int64_t count = L / R;
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < count;
-         j += (int64_t)gridDim.x * blockDim.x) {
-        double2 v[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            v[r] = in[j + r * count];
-            if (MULH) v[r] = cmul(v[r], H[j + r * count]);
+// ---- tiled Stockham FFT ---------------------------------------------------------------------
+// A length-L (power of two) transform is 1-4 global passes.  Pass i is a radix-R_i Stockham step
+// (R_i <= 256): out[(j-k) R + k + y Ns] = DFT_R( in[j + x L/R] * W_{Ns R}^{k x} )[y], k = j mod Ns.
+// A CTA tile is B consecutive j (B*R = 1024 elements, 8 per thread, 128 threads): the tile is
+// gathered in B-element contiguous chunks, the R-point DFTs run cooperatively in shared memory
+// as radix-8/4/2 Stockham sub-passes, and the result is scattered in contiguous chunks.  Many
+// small CTAs are resident per SM, so one CTA's gather latency and barriers overlap another's
+// butterflies (the transform is FP64-issue/latency bound on B200, not HBM bound: ~120 FP64
+// instructions per element per transform against a 64-lane/clk FP64 pipe).  Twiddles come from exact (80-bit,
+// host-computed) tables: a two-level table for W_L and a 4096-entry table for the sub-pass
+// twiddles.  The Bluestein pre-multiply (load), the filter multiply (store of the forward
+// transform) and the chirp post-multiply (store of the inverse transform) are fused in.
+enum { LOAD_PLAIN = 0, LOAD_ALPHA = 1, LOAD_SIGNAL = 2 };
+enum { STORE_PLAIN = 0, STORE_POST = 1, STORE_MULH = 2 };
+
+constexpr int kLog2Tile = 10;  // 1024 complex elements per CTA tile
+constexpr int kTileThreads = (1 << kLog2Tile) / 8;
+constexpr int kMaxLog2R = 8;
+
+struct PassParams {
+    int64_t L;
+    int log2r;       // R = 1 << log2r
+    int log2b;       // B = 1 << log2b
+    int64_t Ns;      // product of the radices of earlier passes
+    int64_t tw_stride;  // L / (Ns R)
+    int split;
+    const double2* whi;
+    const double2* wlo;
+    const double2* wsub;
+    const double2* in;
+    double2* out;
+    const double2* H;      // STORE_MULH
+    const double* src;     // LOAD_ALPHA / LOAD_SIGNAL
+    int c1, c2;            // tensor components packed into (re, im)
+    int64_t M;
+    const double2* chirp;  // LOAD_ALPHA / LOAD_SIGNAL / STORE_POST
+    double2* spec;         // STORE_POST
+};
+
+template <int SGN, int LOAD, int STORE, int RAD>
+__device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
+    const int R = 1 << P.log2r, B = 1 << P.log2b;
+    const int pitch = (B > 1) ? B + 1 : 1;  // padded batch pitch: conflict-free transposing store
+    const int tile = R << P.log2b;
+    const int T = tile >> 3 > 0 ? tile >> 3 : 1;  // active threads (8 elements each)
+    const int tid = threadIdx.x;
+    const bool active = tid < T;
+    const int64_t cnt = P.L >> P.log2r;  // number of j
+    const int64_t num_tiles = cnt >> P.log2b;
+    constexpr int PER = 8 / RAD;  // first-sub-pass butterflies per thread
+    const int nbf = R / RAD;
+
+    auto load = [&](int64_t n) {
+        if (LOAD == LOAD_PLAIN) return P.in[n];
+        double2 v = make_double2(0.0, 0.0);
+        if (n < P.M) {
+            double d1, d2 = 0.0;
+            if (LOAD == LOAD_ALPHA) {
+                // np.diff of the series (_raman.py:282), two tensor components per complex sequence
+                d1 = __ldg(P.src + (n + 1) * 9 + P.c1) - __ldg(P.src + n * 9 + P.c1);
+                d2 = __ldg(P.src + (n + 1) * 9 + P.c2) - __ldg(P.src + n * 9 + P.c2);
+            } else {
+                d1 = __ldg(P.src + n);
+            }
+            const double2 c = __ldg(P.chirp + n);
+            v = make_double2(d1 * c.x - d2 * c.y, d1 * c.y + d2 * c.x);
         }
-        const int64_t k = j & (Ns - 1);
-        if (Ns > 1) {
-            double s, c;
-            sincospi(2.0 * (double)k / (double)(Ns * R), &s, &c);
-            const double2 w1 = make_double2(c, SGN * s);
-            double2 w = w1;
+        return v;
+    };
+    // gather the 8 elements this thread feeds into the first sub-pass of tile `tl`
+    auto gather = [&](int64_t tl, double2* dst) {
+        const int64_t j_base = tl << P.log2b;
 #pragma unroll
-            for (int r = 1; r < R; r++) {
-                v[r] = cmul(v[r], w);
-                if (r + 1 < R) w = cmul(w, w1);
+        for (int t = 0; t < PER; t++) {
+            const int u = tid + t * T;
+            const int i = u >> P.log2b, b = u & (B - 1);
+#pragma unroll
+            for (int q = 0; q < RAD; q++) dst[t * RAD + q] = load(j_base + b + (int64_t)(i + q * nbf) * cnt);
+        }
+    };
+    auto out_index = [&](int64_t j_base, int e, int& b, int& y) {
+        if (P.Ns == 1) {  // out[j R + y]: R contiguous elements per batch member
+            b = e >> P.log2r;
+            y = e & (R - 1);
+            return ((j_base + b) << P.log2r) + y;
+        }
+        // out[(j-k) R + k + y Ns]: B contiguous elements per y
+        b = e & (B - 1);
+        y = e >> P.log2b;
+        const int64_t j = j_base + b;
+        const int64_t k = j & (P.Ns - 1);
+        return ((j - k) << P.log2r) + k + (int64_t)y * P.Ns;
+    };
+
+    for (int64_t tl = blockIdx.x; tl < num_tiles; tl += gridDim.x) {
+        const int64_t j_base = tl << P.log2b;
+        double2 v[8];
+        if (active) gather(tl, v);
+
+        // ---- first sub-pass (pass twiddle, radix RAD, no sub-twiddle) ----
+        if (active) {
+#pragma unroll
+            for (int t = 0; t < PER; t++) {
+                const int u = tid + t * T;
+                const int i = u >> P.log2b, b = u & (B - 1);
+                if (P.Ns > 1) {
+                    const int64_t k = (j_base + b) & (P.Ns - 1);
+#pragma unroll
+                    for (int q = 0; q < RAD; q++) {
+                        const int64_t m = k * (i + q * nbf) * P.tw_stride;
+                        const double2 a = __ldg(P.whi + (m >> P.split));
+                        const double2 bb = __ldg(P.wlo + (m & (((int64_t)1 << P.split) - 1)));
+                        double2 w = cmul(a, bb);
+                        if (SGN > 0) w.y = -w.y;
+                        v[t * RAD + q] = cmul(v[t * RAD + q], w);
+                    }
+                }
+                if (RAD == 8) dft8<SGN>(v + RAD * t);
+                if (RAD == 4) dft4<SGN>(v + RAD * t);
+                if (RAD == 2) dft2<SGN>(v + RAD * t);
+#pragma unroll
+                for (int q = 0; q < RAD; q++) S[(i * RAD + q) * pitch + b] = v[t * RAD + q];
             }
         }
-        if (R == 8) dft8<SGN>(v);
-        if (R == 4) dft4<SGN>(v);
-        if (R == 2) dft2<SGN>(v);
-        const int64_t j0 = (j - k) * R + k;
+        double2 hv[8];
+        if (STORE == STORE_MULH && active) {  // filter values for the store phase: issue early
 #pragma unroll
-        for (int r = 0; r < R; r++) out[j0 + r * Ns] = v[r];
+            for (int t = 0; t < 8; t++) {
+                int b, y;
+                hv[t] = __ldg(P.H + out_index(j_base, tid + t * T, b, y));
+            }
+        }
+        __syncthreads();
+        // ---- remaining radix-8 sub-passes, in place through registers ----
+        const int nb = R >> 3;
+        for (int ns = RAD; ns < R; ns <<= 3) {
+            int i = 0, b = 0, kk = 0;
+            if (active) {
+                i = tid >> P.log2b;
+                b = tid & (B - 1);
+                kk = i & (ns - 1);
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = S[(i + q * nb) * pitch + b];
+                double2 w1 = __ldg(P.wsub + kk * (4096 / (ns * 8)));
+                if (SGN > 0) w1.y = -w1.y;
+                double2 w = w1;
+#pragma unroll
+                for (int q = 1; q < 8; q++) {
+                    v[q] = cmul(v[q], w);
+                    if (q < 7) w = cmul(w, w1);
+                }
+                dft8<SGN>(v);
+            }
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) S[((i - kk) * 8 + kk + q * ns) * pitch + b] = v[q];
+            }
+            __syncthreads();
+        }
+        // ---- scatter to global ----
+        if (active) {
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                int b, y;
+                const int64_t gidx = out_index(j_base, tid + t * T, b, y);
+                double2 val = S[y * pitch + b];
+                if (STORE == STORE_PLAIN) {
+                    P.out[gidx] = val;
+                } else if (STORE == STORE_MULH) {
+                    P.out[gidx] = cmul(val, hv[t]);
+                } else if (gidx < P.M) {
+                    P.spec[gidx] = cmul(val, __ldg(P.chirp + gidx));
+                }
+            }
+        }
+        __syncthreads();  // S is rewritten by the next tile
     }
 }
 
-template <int SGN, bool MULH>
-static int launch_pass(int R, const double2* in, double2* out, const double2* H, int64_t L, int64_t Ns, int sms,
-                       cudaStream_t stream) {
-    const int64_t count = L / R;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((count + 255) / 256, (int64_t)sms * 16));
-    if (R == 8) fft_pass_kernel<8, SGN, MULH><<<grid, 256, 0, stream>>>(in, out, H, L, Ns);
-    if (R == 4) fft_pass_kernel<4, SGN, MULH><<<grid, 256, 0, stream>>>(in, out, H, L, Ns);
-    if (R == 2) fft_pass_kernel<2, SGN, MULH><<<grid, 256, 0, stream>>>(in, out, H, L, Ns);
+template <int SGN, int LOAD, int STORE>
+__global__ void __launch_bounds__(kTileThreads, STORE == STORE_MULH ? 4 : 6) fft_tile_kernel(PassParams P) {
+    extern __shared__ __align__(16) unsigned char fft_smem[];
+    double2* S = reinterpret_cast<double2*>(fft_smem);
+    const int rem = P.log2r % 3;
+    if (rem == 0) fft_tile_body<SGN, LOAD, STORE, 8>(P, S);
+    else if (rem == 2) fft_tile_body<SGN, LOAD, STORE, 4>(P, S);
+    else fft_tile_body<SGN, LOAD, STORE, 2>(P, S);
+}
+
+struct FftIo {
+    int load = LOAD_PLAIN;
+    int store = STORE_PLAIN;
+    const double2* H = nullptr;
+    const double* src = nullptr;
+    int c1 = 0, c2 = 0;
+    double2* spec = nullptr;
+};
+
+template <int SGN, int LOAD, int STORE>
+static int launch_tile_pass(const rn_spectrum_plan* p, const PassParams& P, cudaStream_t stream) {
+    const int R = 1 << P.log2r, B = 1 << P.log2b;
+    const int pitch = (B > 1) ? B + 1 : 1;
+    const size_t smem = (size_t)R * pitch * sizeof(double2);
+    const int64_t tiles = (P.L >> P.log2r) >> P.log2b;
+    auto kern = fft_tile_kernel<SGN, LOAD, STORE>;
+    (void)p;
+    const int64_t grid = std::min<int64_t>(tiles, (int64_t)1 << 30);  // one tile per CTA; many small CTAs per SM
+    kern<<<(unsigned)grid, kTileThreads, smem, stream>>>(P);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     return RN_OK;
 }
 
-// Full length-L FFT, ping-ponging between a and b; *result receives the buffer holding the output.
+// Full length-L transform: `first` is read by the first pass (with io.load); passes ping-pong
+// between the plan buffers (never writing the buffer being read); the last pass writes `last_out`
+// if given (must not be a plan work buffer), else the next ping-pong buffer.  *result (optional)
+// receives the buffer holding the output.
 template <int SGN>
-static int fft_pow2(double2* a, double2* b, const double2* H, int64_t L, int sms, cudaStream_t stream,
-                    double2** result) {
-    int log2l = 0;
-    while (((int64_t)1 << log2l) < L) log2l++;
+static int fft_run(const rn_spectrum_plan* p, const double2* first, double2* last_out, const FftIo& io,
+                   cudaStream_t stream, double2** result = nullptr) {
     int64_t Ns = 1;
-    double2 *src = a, *dst = b;
-    bool first = true;
-    int rem = log2l;
-    while (rem > 0) {
-        int R = 8;
-        if (rem % 3 == 1) R = 2;       // take the odd factor first (twiddle-free while Ns == 1)
-        else if (rem % 3 == 2) R = 4;
-        int rc;
-        if (first && H != nullptr) rc = launch_pass<SGN, true>(R, src, dst, H, L, Ns, sms, stream);
-        else rc = launch_pass<SGN, false>(R, src, dst, nullptr, L, Ns, sms, stream);
-        if (rc != RN_OK) return rc;
-        first = false;
-        Ns *= R;
-        rem -= (R == 8) ? 3 : (R == 4 ? 2 : 1);
-        std::swap(src, dst);
+    const double2* src = first;
+    for (int i = 0; i < p->num_passes; i++) {
+        const bool is_first = (i == 0), is_last = (i == p->num_passes - 1);
+        PassParams P;
+        P.L = p->L;
+        P.log2r = p->pass_log2r[i];
+        int log2b = kLog2Tile - P.log2r;
+        const int log2cnt = p->log2l - P.log2r;
+        if (log2b > log2cnt) log2b = log2cnt;
+        if (log2b < 0) log2b = 0;
+        P.log2b = log2b;
+        P.Ns = Ns;
+        P.tw_stride = p->L / (Ns << P.log2r);
+        P.split = p->split;
+        P.whi = p->d_whi;
+        P.wlo = p->d_wlo;
+        P.wsub = p->d_wsub;
+        P.in = src;
+        double2* dst = (is_last && last_out) ? last_out : ((src == p->d_buf0) ? p->d_buf1 : p->d_buf0);
+        P.out = dst;
+        P.H = io.H;
+        P.src = io.src;
+        P.c1 = io.c1;
+        P.c2 = io.c2;
+        P.M = p->M;
+        P.chirp = p->d_chirp;
+        P.spec = io.spec;
+        const int load = is_first ? io.load : LOAD_PLAIN;
+        const int store = is_last ? io.store : STORE_PLAIN;
+        int rc = RN_ERR_UNSUPPORTED;
+#define RN_PASS(LD, ST) \
+    if (load == LD && store == ST) rc = launch_tile_pass<SGN, LD, ST>(p, P, stream);
+        RN_PASS(LOAD_PLAIN, STORE_PLAIN)
+        RN_PASS(LOAD_PLAIN, STORE_POST)
+        RN_PASS(LOAD_PLAIN, STORE_MULH)
+        RN_PASS(LOAD_ALPHA, STORE_PLAIN)
+        RN_PASS(LOAD_ALPHA, STORE_MULH)
+        RN_PASS(LOAD_SIGNAL, STORE_PLAIN)
+        RN_PASS(LOAD_SIGNAL, STORE_MULH)
+#undef RN_PASS
+        if (rc != RN_OK) {
+            if (rc == RN_ERR_UNSUPPORTED) set_error("unsupported FFT pass configuration");
+            return rc;
+        }
+        Ns <<= P.log2r;
+        src = dst;
+        if (result) *result = dst;
     }
-    *result = src;
     return RN_OK;
 }
 
-// ---- Bluestein pre/post kernels -----------------------------------------------------------
+// ---- Bluestein helper kernels ---------------------------------------------------------------
+
+// chirp table c[n] = exp(-i*pi*n^2/M), n < M
+__global__ void chirp_table_kernel(double2* __restrict__ out, int64_t M) {
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < M; n += (int64_t)gridDim.x * blockDim.x)
+        out[n] = chirp(n, M);
+}
 
 // h[m] = exp(+i*pi*m^2/M) for |m| < M, stored circularly in a length-L array
-__global__ void chirp_filter_kernel(double2* __restrict__ out, int64_t M, int64_t L) {
+__global__ void chirp_filter_kernel(double2* __restrict__ out, const double2* __restrict__ chirp_table, int64_t M,
+                                    int64_t L) {
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < L; idx += (int64_t)gridDim.x * blockDim.x) {
         int64_t m = -1;
         if (idx < M) m = idx;
         else if (L - idx < M) m = L - idx;
         double2 v = make_double2(0.0, 0.0);
         if (m >= 0) {
-            const double2 c = chirp(m, M);
+            const double2 c = chirp_table[m];
             v = make_double2(c.x, -c.y);
         }
         out[idx] = v;
     }
-}
-
-// a[n] = (d1[n] + i d2[n]) * chirp(n) for n < M, 0 for M <= n < L, where d = diff of the
-// polarizability series (np.diff, _raman.py:282) for tensor components (c1, c2).
-// MODE 0: alpha series (stride 9, differences); MODE 1: a plain real signal (no diff, imag = 0).
-template <int MODE>
-__global__ void bluestein_prep_kernel(const double* __restrict__ src, int c1, int c2, double2* __restrict__ out,
-                                      int64_t M, int64_t L) {
-    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.x * blockDim.x) {
-        double2 v = make_double2(0.0, 0.0);
-        if (n < M) {
-            double d1, d2;
-            if (MODE == 0) {
-                d1 = src[(n + 1) * 9 + c1] - src[n * 9 + c1];
-                d2 = src[(n + 1) * 9 + c2] - src[n * 9 + c2];
-            } else {
-                d1 = src[n];
-                d2 = 0.0;
-            }
-            const double2 c = chirp(n, M);
-            v = make_double2(d1 * c.x - d2 * c.y, d1 * c.y + d2 * c.x);
-        }
-        out[n] = v;
-    }
-}
-
-// spec[k] = chirp(k) * y[k], k < M   (the 1/L of the inverse FFT is applied by the consumer)
-__global__ void bluestein_post_kernel(const double2* __restrict__ y, double2* __restrict__ spec, int64_t M) {
-    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < M; k += (int64_t)gridDim.x * blockDim.x)
-        spec[k] = cmul(y[k], chirp(k, M));
 }
 
 // Energies sum_n s_n^2 of the seven signals of measure() (MODE 0) or of one real signal (MODE 1).
@@ -249,10 +434,23 @@ __global__ void __launch_bounds__(256) energy_partial_kernel(const double* __res
     }
 }
 
-__global__ void energy_final_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ energy) {
+__global__ void __launch_bounds__(256) energy_final_kernel(const double* __restrict__ partial, int blocks,
+                                                           double* __restrict__ energy) {
+    // fixed-shape tree: thread t sums partials t, t+256, ...; then warp shuffles; then 8 warps
+    __shared__ double sm[8][7];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+        double v = 0;
+        for (int b = threadIdx.x; b < blocks; b += 256) v += partial[(int64_t)b * 8 + q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) sm[warp][q] = v;
+    }
+    __syncthreads();
     if (threadIdx.x < 7) {
         double v = 0;
-        for (int b = 0; b < blocks; b++) v += partial[(int64_t)b * 8 + threadIdx.x];
+        for (int w = 0; w < 8; w++) v += sm[w][threadIdx.x];
         energy[threadIdx.x] = v;
     }
 }
@@ -333,19 +531,20 @@ static int grid_for(int64_t n, int sms) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16));
 }
 
-// chirp-z transform of the sequence already prepared in plan->d_buf0; writes spec_out[0..M)
-static int bluestein_transform(rn_spectrum_plan* p, double2* spec_out, cudaStream_t stream) {
+// chirp-z transform of one (packed) sequence: forward FFT with the Bluestein pre-multiply fused
+// into the first pass' load, inverse FFT with the filter multiply fused into its first load and
+// the chirp post-multiply fused into its last store.  Writes spec_out[0..M).
+static int bluestein_transform(rn_spectrum_plan* p, const FftIo& in_io, double2* spec_out, cudaStream_t stream) {
     double2* fwd = nullptr;
-    int rc = fft_pow2<-1>(p->d_buf0, p->d_buf1, nullptr, p->L, p->sm_count, stream, &fwd);
+    FftIo fio = in_io;
+    fio.store = STORE_MULH;  // multiply by the filter spectrum while storing the forward transform
+    fio.H = p->d_filter;
+    int rc = fft_run<-1>(p, nullptr, nullptr, fio, stream, &fwd);
     if (rc != RN_OK) return rc;
-    double2* other = (fwd == p->d_buf0) ? p->d_buf1 : p->d_buf0;
-    double2* inv = nullptr;
-    rc = fft_pow2<+1>(fwd, other, p->d_filter, p->L, p->sm_count, stream, &inv);
-    if (rc != RN_OK) return rc;
-    bluestein_post_kernel<<<grid_for(p->M, p->sm_count), 256, 0, stream>>>(inv, spec_out, p->M);
-    RN_LAUNCHED();
-    RN_CUDA(cudaGetLastError());
-    return RN_OK;
+    FftIo io;
+    io.store = STORE_POST;
+    io.spec = spec_out;
+    return fft_run<+1>(p, fwd, nullptr, io, stream);
 }
 
 static void destroy_plan(rn_spectrum_plan* p) {
@@ -354,9 +553,20 @@ static void destroy_plan(rn_spectrum_plan* p) {
     cudaFree(p->d_buf1);
     cudaFree(p->d_filter);
     cudaFree(p->d_spec);
+    cudaFree(p->d_chirp);
+    cudaFree(p->d_whi);
+    cudaFree(p->d_wlo);
+    cudaFree(p->d_wsub);
     cudaFree(p->d_partial);
     cudaFree(p->d_energy);
     delete p;
+}
+
+// exp(-2 pi i num/den) in 80-bit arithmetic, with exact octant symmetry handling left to cosl/sinl
+static double2 unit_root(int64_t num, int64_t den) {
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    const long double ang = two_pi * (long double)num / (long double)den;
+    return make_double2((double)cosl(ang), (double)-sinl(ang));
 }
 
 }  // namespace rn
@@ -389,17 +599,36 @@ extern "C" int rn_spectrum_plan_create(int64_t num_frames, int device, rn_spectr
     p->S = num_frames;
     p->M = num_frames - 1;
     int64_t L = 8;
-    while (L < 2 * p->M - 1) L <<= 1;
+    int log2l = 3;
+    while (L < 2 * p->M - 1) {
+        L <<= 1;
+        log2l++;
+    }
+    RN_CHECK_ARG(log2l <= 30, "series too long for one spectrum plan (%lld frames)", (long long)num_frames);
     p->L = L;
+    p->log2l = log2l;
+    // pass structure: sub-transforms of at most 256 points (>= 64-byte global chunks), as even as possible
+    p->num_passes = (log2l + kMaxLog2R - 1) / kMaxLog2R;
+    for (int i = 0, rem = log2l; i < p->num_passes; i++) {
+        const int left = p->num_passes - i;
+        p->pass_log2r[i] = (rem + left - 1) / left;
+        rem -= p->pass_log2r[i];
+    }
+    p->split = log2l / 2;
     p->energy_blocks = (int)std::min<int64_t>((p->M + 255) / 256, (int64_t)p->sm_count * 4);
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void** ptr, size_t bytes) {
         if (err == cudaSuccess) err = cudaMalloc(ptr, bytes);
     };
+    const int64_t n_hi = L >> p->split, n_lo = (int64_t)1 << p->split;
     alloc((void**)&p->d_buf0, sizeof(double2) * L);
     alloc((void**)&p->d_buf1, sizeof(double2) * L);
     alloc((void**)&p->d_filter, sizeof(double2) * L);
     alloc((void**)&p->d_spec, sizeof(double2) * 3 * p->M);
+    alloc((void**)&p->d_chirp, sizeof(double2) * p->M);
+    alloc((void**)&p->d_whi, sizeof(double2) * n_hi);
+    alloc((void**)&p->d_wlo, sizeof(double2) * n_lo);
+    alloc((void**)&p->d_wsub, sizeof(double2) * 4096);
     alloc((void**)&p->d_partial, sizeof(double) * 8 * p->energy_blocks);
     alloc((void**)&p->d_energy, sizeof(double) * 8);
     if (err != cudaSuccess) {
@@ -409,14 +638,29 @@ extern "C" int rn_spectrum_plan_create(int64_t num_frames, int device, rn_spectr
         cudaGetLastError();
         return RN_ERR_OUT_OF_MEMORY;
     }
-    // filter spectrum H = FFT_L(h), computed once per plan
-    chirp_filter_kernel<<<grid_for(L, p->sm_count), 256>>>(p->d_buf0, p->M, L);
+    {
+        std::vector<double2> whi((size_t)n_hi), wlo((size_t)n_lo), wsub((size_t)4096);
+        for (int64_t a = 0; a < n_hi; a++) whi[(size_t)a] = unit_root(a << p->split, L);
+        for (int64_t b = 0; b < n_lo; b++) wlo[(size_t)b] = unit_root(b, L);
+        for (int m = 0; m < 4096; m++) wsub[(size_t)m] = unit_root(m, 4096);
+        cudaError_t e1 = cudaMemcpy(p->d_whi, whi.data(), sizeof(double2) * n_hi, cudaMemcpyHostToDevice);
+        if (e1 == cudaSuccess) e1 = cudaMemcpy(p->d_wlo, wlo.data(), sizeof(double2) * n_lo, cudaMemcpyHostToDevice);
+        if (e1 == cudaSuccess) e1 = cudaMemcpy(p->d_wsub, wsub.data(), sizeof(double2) * 4096, cudaMemcpyHostToDevice);
+        if (e1 != cudaSuccess) {
+            set_error("twiddle table upload failed: %s", cudaGetErrorString(e1));
+            destroy_plan(p);
+            return RN_ERR_CUDA;
+        }
+    }
+    // chirp table, then the filter spectrum H = FFT_L(h) — computed once per plan
+    chirp_table_kernel<<<grid_for(p->M, p->sm_count), 256>>>(p->d_chirp, p->M);
     RN_LAUNCHED();
-    double2* res = nullptr;
-    int rc = fft_pow2<-1>(p->d_buf0, p->d_buf1, nullptr, L, p->sm_count, nullptr, &res);
+    chirp_filter_kernel<<<grid_for(L, p->sm_count), 256>>>(p->d_buf0, p->d_chirp, p->M, L);
+    RN_LAUNCHED();
+    FftIo io;
+    int rc = fft_run<-1>(p, p->d_buf0, p->d_filter, io, nullptr);
     if (rc == RN_OK) {
-        cudaError_t e2 = cudaMemcpyAsync(p->d_filter, res, sizeof(double2) * L, cudaMemcpyDeviceToDevice, nullptr);
-        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(nullptr);
+        cudaError_t e2 = cudaStreamSynchronize(nullptr);
         if (e2 != cudaSuccess) {
             set_error("spectrum plan initialisation failed: %s", cudaGetErrorString(e2));
             rc = RN_ERR_CUDA;
@@ -454,15 +698,17 @@ extern "C" int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, dou
 
     energy_partial_kernel<0><<<plan->energy_blocks, 256, 0, s>>>(d_alpha, M, plan->d_partial);
     RN_LAUNCHED();
-    energy_final_kernel<<<1, 32, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
+    energy_final_kernel<<<1, 256, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
     RN_LAUNCHED();
     // component pairs: (xx, yy), (zz, xy), (yz, xz)  — the upper triangle used at _raman.py:284-296
     const int pairs[3][2] = {{0, 4}, {8, 1}, {5, 2}};
     for (int b = 0; b < 3; b++) {
-        bluestein_prep_kernel<0><<<grid_for(L, plan->sm_count), 256, 0, s>>>(d_alpha, pairs[b][0], pairs[b][1],
-                                                                            plan->d_buf0, M, L);
-        RN_LAUNCHED();
-        int rc = bluestein_transform(plan, plan->d_spec + (int64_t)b * M, s);
+        FftIo io;
+        io.load = LOAD_ALPHA;
+        io.src = d_alpha;
+        io.c1 = pairs[b][0];
+        io.c2 = pairs[b][1];
+        int rc = bluestein_transform(plan, io, plan->d_spec + (int64_t)b * M, s);
         if (rc != RN_OK) return rc;
     }
     SpectrumParams prm;
@@ -489,15 +735,29 @@ extern "C" int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal
     const int64_t points = (M + 1) / 2;
     energy_partial_kernel<1><<<plan->energy_blocks, 256, 0, s>>>(d_signal, M, plan->d_partial);
     RN_LAUNCHED();
-    energy_final_kernel<<<1, 32, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
+    energy_final_kernel<<<1, 256, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
     RN_LAUNCHED();
-    bluestein_prep_kernel<1><<<grid_for(L, plan->sm_count), 256, 0, s>>>(d_signal, 0, 0, plan->d_buf0, M, L);
-    RN_LAUNCHED();
-    int rc = bluestein_transform(plan, plan->d_spec, s);
+    FftIo io;
+    io.load = LOAD_SIGNAL;
+    io.src = d_signal;
+    int rc = bluestein_transform(plan, io, plan->d_spec, s);
     if (rc != RN_OK) return rc;
     signal_combine_kernel<<<grid_for(points, plan->sm_count), 256, 0, s>>>(plan->d_spec, plan->d_energy, M, L, points,
                                                                           sampling_rate, d_wavenumbers, d_intensities);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     return RN_OK;
+}
+
+// Test hook (not in the public header): plain length-L transform of plan->L complex values,
+// sign -1 forward / +1 inverse (unscaled).  d_out must not alias d_in.
+extern "C" int rn_debug_fft(rn_spectrum_plan* plan, const double* d_in, double* d_out, int sign, void* stream) {
+    RN_CHECK_ARG(plan && d_in && d_out, "null pointer");
+    DeviceGuard guard(plan->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    RN_CUDA(cudaMemcpyAsync(plan->d_buf1, d_in, sizeof(double2) * plan->L, cudaMemcpyDeviceToDevice, s));
+    FftIo io;
+    // the first pass reads d_buf1; intermediate passes ping-pong and never write the buffer being read
+    if (sign < 0) return fft_run<-1>(plan, plan->d_buf1, reinterpret_cast<double2*>(d_out), io, s);
+    return fft_run<+1>(plan, plan->d_buf1, reinterpret_cast<double2*>(d_out), io, s);
 }

@@ -146,3 +146,31 @@ def test_spectrum_error_behaviour():
         rb.convolve_spectrum(np.array([1.0, 2.0, 3.0]), [0, 3, 0], "gaussian", 5)
     with pytest.raises(ValueError, match=r"intensities has wrong shape: \(2,\) != \(3,\)"):
         rb.convolve_spectrum(np.array([1.0, 2.0, 3.0]), np.array([0.0, 3.0]), "gaussian", 5)
+
+
+@pytest.mark.parametrize("log2l", [3, 4, 5, 6, 7, 9, 10, 12, 13, 14, 16, 17, 20, 21, 22])
+def test_tiled_fft_against_torch(log2l):
+    """The hand-written tiled Stockham FFT (1, 2 and 3 global passes; first sub-pass radix 2, 4
+    and 8) against torch.fft (cuFFT) in both directions."""
+    import ctypes
+
+    from ramannoodle_b200 import _lib
+    from ramannoodle_b200.spectrum import _get_plan
+
+    length = 1 << log2l
+    frames = (length >> 1) + 1  # M = L/2 -> Bluestein length L
+    plan = _get_plan(frames, 0)
+    gen = torch.Generator("cuda:0").manual_seed(log2l)
+    x = torch.randn(length, 2, dtype=torch.float64, device="cuda:0", generator=gen)
+    out = torch.empty_like(x)
+    lib = _lib.lib()
+    lib.rn_debug_fft.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    lib.rn_debug_fft.restype = ctypes.c_int
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    xc = torch.view_as_complex(x)
+    for sign, ref in ((-1, torch.fft.fft(xc)), (1, torch.fft.ifft(xc) * length)):
+        assert lib.rn_debug_fft(plan.handle, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), sign,
+                                stream) == 0
+        got = torch.view_as_complex(out)
+        err = float((got - ref).abs().max() / ref.abs().max())
+        assert err < 1e-13, f"L=2^{log2l} sign={sign}: {err}"

@@ -83,6 +83,17 @@ struct rn_model {
     int64_t v_cols = 0;               // Kv: columns of the dense basis (K padded to 16)
     int64_t dense_pad = 0;            // Jd_pad: dense DOFs padded to the J tile
     int affine_kp = 0;                // k-step pairs per warp for the TMA affine kernel (0 = ineligible)
+
+    // truncated-power form of the dense DOFs (chained-DMMA epilogue): B_j(x) = const_j +
+    // sum_{m=1..D} g_{j,m} (x-x0_j)^m + sum_i sum_m d_{j,i,m} max(x-b_{j,i},0)^m
+    int tp_mode = 0;                  // 0 = unavailable, 1 = top power per break (true splines), 2 = all powers
+    int tp_breaks = 0;                // break slots per DOF (padded with +inf)
+    int tp_features = 0;              // features per DOF
+    double alpha0_tp[9] = {0};        // alpha0 + sum_j const_j
+    double* d_tp_x0 = nullptr;        // (Jd_pad)
+    double* d_tp_brk = nullptr;       // (Jd_pad, tp_breaks)
+    double* d_tp_c8 = nullptr;        // (Jd_pad, tp_features, 8) tensor components 0..7
+    double* d_tp_c9 = nullptr;        // (Jd_pad, tp_features)    tensor component 8
 };
 
 namespace rn {
@@ -92,6 +103,8 @@ int launch_affine(const rn_model* m, const double* d_in, bool wrap, int64_t num_
                   cudaStream_t stream);
 int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
                  double* d_alpha, cudaStream_t stream);
+int launch_dense_v1(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
+                    double* d_alpha, cudaStream_t stream);
 int launch_fill_alpha0(const rn_model* m, int64_t num_frames, double* d_alpha, cudaStream_t stream);
 
 }  // namespace rn

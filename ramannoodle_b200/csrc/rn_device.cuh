@@ -1,0 +1,41 @@
+// Device helpers shared by the polarizability kernels (sm_100a).
+#pragma once
+
+#include "rn_common.cuh"
+
+namespace rn {
+
+struct Alpha0 {
+    double v[9];
+};
+
+// wrap(pos - ref) into (-0.5, 0.5]: apply_pbc_displacement(calc_displacement(...)) of the
+// reference (structure/utils.py:46,132-135); ties resolve to +0.5 exactly as `d % 1 > 0.5`.
+__device__ __forceinline__ double wrap_disp(double pos, double ref) {
+    const double d = pos - ref;
+    return d - ceil(d - 0.5);
+}
+
+// FP64 tensor-pipe MMA (SASS: DMMA.8x8x4).  A 8x4 row-major: lane holds A[lane>>2][lane&3];
+// B 4x8 col-major: lane holds B[lane&3][lane>>2]; C 8x8: lane holds C[lane>>2][2*(lane&3)+{0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+}  // namespace rn

@@ -13,6 +13,7 @@
 // Re-association only: measured head-room vs the reference is ~1e-14 relative.
 #include <cmath>
 #include <cstring>
+#include <limits>
 
 #include "rn_common.cuh"
 
@@ -134,6 +135,10 @@ static void destroy_model(rn_model* m) {
     cudaFree(m->d_piece_off);
     cudaFree(m->d_breaks);
     cudaFree(m->d_pieces);
+    cudaFree(m->d_tp_x0);
+    cudaFree(m->d_tp_brk);
+    cudaFree(m->d_tp_c8);
+    cudaFree(m->d_tp_c9);
     delete m;
 }
 
@@ -323,12 +328,94 @@ extern "C" int rn_model_create(const double* h_ref_positions, int64_t num_atoms,
         piece_off.push_back((int32_t)(pieces.size() / rec));
     }
 
+    // ---- truncated-power tables for the chained-DMMA epilogue ----
+    std::vector<double> tp_x0, tp_brk, tp_c8, tp_c9;
+    if (jd > 0 && dense_degree >= 1 && dense_degree <= 3 && dense_max_pieces - 1 <= 3) {
+        const int D = dense_degree;
+        const int nbk = dense_max_pieces - 1;
+        // jump polynomials at every interior break, in 80-bit arithmetic
+        struct Jumps {
+            std::vector<LD> d;  // (breaks, D+1, 9)
+        };
+        std::vector<Jumps> jumps((size_t)jd);
+        bool spline_only = true;
+        for (int64_t i = 0; i < jd; i++) {
+            const PiecewisePoly& pp = pps[(size_t)dense_ids[(size_t)i]];
+            const int P = pp.pieces(), dj = pp.degree;
+            jumps[(size_t)i].d.assign((size_t)std::max(P - 1, 0) * (D + 1) * 9, 0.0L);
+            LD scale = 0.0L;  // magnitude of the spline over its knot span
+            const LD span = (P > 1) ? 2.0L * std::fabs((LD)pp.breaks.back() - (LD)pp.x0[0]) : 1.0L;  // ~ knot span
+            for (int p = 0; p < P; p++)
+                for (int mm = 0; mm <= dj; mm++)
+                    for (int q = 0; q < 9; q++)
+                        scale = std::max(scale, std::fabs(pp.coefs[((size_t)p * (dj + 1) + mm) * 9 + q]) * powl(span, mm));
+            for (int b = 0; b + 1 < P; b++) {
+                // Delta_b(u) = poly_{b+1}(u) - poly_b(u + h), h = x0_{b+1} - x0_b (binomial shift)
+                const LD h = (LD)pp.x0[(size_t)b + 1] - (LD)pp.x0[(size_t)b];
+                for (int q = 0; q < 9; q++) {
+                    for (int mm = 0; mm <= dj; mm++) {
+                        LD shifted = 0.0L;  // coefficient of u^mm in poly_b(u + h)
+                        LD binom = 1.0L;    // C(r, mm) built incrementally over r
+                        for (int r = mm; r <= dj; r++) {
+                            if (r > mm) binom = binom * (LD)r / (LD)(r - mm);
+                            shifted += pp.coefs[((size_t)b * (dj + 1) + r) * 9 + q] * binom * powl(h, r - mm);
+                        }
+                        const LD dv = pp.coefs[((size_t)(b + 1) * (dj + 1) + mm) * 9 + q] - shifted;
+                        jumps[(size_t)i].d[((size_t)b * (D + 1) + mm) * 9 + q] = dv;
+                        if (mm < D && std::fabs(dv) * powl(span, mm) > 1e-13L * scale) spline_only = false;
+                    }
+                }
+            }
+        }
+        const int per_break = spline_only ? 1 : (D + 1);
+        const int nf = D + nbk * per_break;
+        if (nf <= 12) {
+            m->tp_mode = spline_only ? 1 : 2;
+            m->tp_breaks = nbk;
+            m->tp_features = nf;
+            const double inf = std::numeric_limits<double>::infinity();
+            tp_x0.assign((size_t)m->dense_pad, 0.0);
+            tp_brk.assign((size_t)m->dense_pad * std::max(nbk, 1), inf);
+            tp_c8.assign((size_t)m->dense_pad * nf * 8, 0.0);
+            tp_c9.assign((size_t)m->dense_pad * nf, 0.0);
+            std::vector<LD> a0tp(9);
+            for (int q = 0; q < 9; q++) a0tp[q] = alpha0[q];
+            for (int64_t i = 0; i < jd; i++) {
+                const int64_t j = dense_ids[(size_t)i];
+                const PiecewisePoly& pp = pps[(size_t)j];
+                const LD w = h_weight[j];
+                const int dj = pp.degree, P = pp.pieces();
+                tp_x0[(size_t)i] = pp.x0[0];
+                for (int b = 0; b + 1 < P; b++) tp_brk[(size_t)i * std::max(nbk, 1) + b] = pp.breaks[(size_t)b];
+                auto put = [&](int f, int q, LD v) {
+                    if (q < 8) tp_c8[((size_t)i * nf + f) * 8 + q] = (double)v;
+                    else tp_c9[(size_t)i * nf + f] = (double)v;
+                };
+                for (int q = 0; q < 9; q++) {
+                    a0tp[q] += w * pp.coefs[(size_t)0 * 9 + q];  // constant term of the first piece
+                    for (int mm = 1; mm <= dj; mm++) put(mm - 1, q, w * pp.coefs[((size_t)mm) * 9 + q]);
+                    for (int b = 0; b + 1 < P; b++) {
+                        if (spline_only) {
+                            put(D + b, q, w * jumps[(size_t)i].d[((size_t)b * (D + 1) + D) * 9 + q]);
+                        } else {
+                            for (int mm = 0; mm <= D; mm++)
+                                put(D + b * (D + 1) + mm, q, w * jumps[(size_t)i].d[((size_t)b * (D + 1) + mm) * 9 + q]);
+                        }
+                    }
+                }
+            }
+            for (int q = 0; q < 9; q++) m->alpha0_tp[q] = (double)a0tp[q];
+        }
+    }
+
     int rc = RN_OK;
     if ((rc = upload(&m->d_ref_wrapped, ref)) != RN_OK || (rc = upload(&m->d_zero_ref, zero_ref)) != RN_OK ||
         (rc = upload(&m->d_g_frac, g_frac_d)) != RN_OK || (rc = upload(&m->d_g_cart, g_cart_d)) != RN_OK ||
         (rc = upload(&m->d_v_frac, v_frac)) != RN_OK || (rc = upload(&m->d_v_cart, v_cart)) != RN_OK ||
         (rc = upload(&m->d_piece_off, piece_off)) != RN_OK || (rc = upload(&m->d_breaks, breaks)) != RN_OK ||
-        (rc = upload(&m->d_pieces, pieces)) != RN_OK) {
+        (rc = upload(&m->d_pieces, pieces)) != RN_OK || (rc = upload(&m->d_tp_x0, tp_x0)) != RN_OK ||
+        (rc = upload(&m->d_tp_brk, tp_brk)) != RN_OK || (rc = upload(&m->d_tp_c8, tp_c8)) != RN_OK ||
+        (rc = upload(&m->d_tp_c9, tp_c9)) != RN_OK) {
         destroy_model(m);
         return rc;
     }

@@ -17,26 +17,9 @@
 //                          the piecewise-polynomial spline evaluation + 3x3 reduction fused as
 //                          the epilogue (amplitudes never touch HBM).  FP64-pipe-bound:
 //                          2*3N*J flops per frame.
-#include "rn_common.cuh"
+#include "rn_device.cuh"
 
 namespace rn {
-
-struct Alpha0 {
-    double v[9];
-};
-
-// wrap(pos - ref) into (-0.5, 0.5]: apply_pbc_displacement(calc_displacement(...)) of the
-// reference (structure/utils.py:46,132-135); ties resolve to +0.5 exactly as `d % 1 > 0.5`.
-__device__ __forceinline__ double wrap_disp(double pos, double ref) {
-    const double d = pos - ref;
-    return d - ceil(d - 0.5);
-}
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(c0), "+d"(c1)
-        : "d"(a), "d"(b));
-}
 
 // ------------------------------------------------------------------------------------
 // generic affine kernel: one warp per group of 8 frames, A fragments straight from global
@@ -82,8 +65,6 @@ __global__ void __launch_bounds__(256) affine_generic_kernel(const double* __res
 // TMA affine kernel
 // ------------------------------------------------------------------------------------
 constexpr int kRedStride = 12;  // doubles per (warp, frame) slot in the cross-warp reduction buffer
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -402,18 +383,6 @@ constexpr int kKC = 16;   // K elements per pipeline chunk
 constexpr int kRS = 20;   // padded smem row stride (doubles): conflict-free fragment loads
 constexpr int kDStages = 3;
 
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 template <int DEG, bool WRAP, bool ALIGN16>
 __global__ void __launch_bounds__(256, 1)
     dense_kernel(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ V,
@@ -602,8 +571,8 @@ static int launch_dense_deg(const rn_model* m, const double* d_in, bool wrap, bo
     return RN_OK;
 }
 
-int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
-                 double* d_alpha, cudaStream_t stream) {
+int launch_dense_v1(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
+                    double* d_alpha, cudaStream_t stream) {
     if (num_frames == 0) return RN_OK;
     switch (m->dense_degree) {
         case 0:

@@ -1,21 +1,22 @@
-// Dense polarizability kernel, second generation (sm_100a).
+// Dense polarizability kernels (sm_100a): general splines.
 //
 //   alpha_s (+)= sum_{j in dense DOFs} w_j B_j( v_j . vec(wrap(p_s - p_ref) L) )
 //   (ramannoodle/pmodel/_interpolation.py:233-252: one einsum + one BSpline call per DOF)
 //
-// One persistent CTA per SM, 8 warps.  A work tile is FT frames x all dense DOFs; DOFs are
-// walked in tiles of 64, K = 3N in chunks of 16 through a 4-stage cp.async ring:
-//   iteration it:  wait(chunk it+1) | barrier | issue(chunk it+3) | wrap(chunk it+1) | MMA(chunk it)
-// * wrap: the raw fractional positions of a landed chunk are replaced in shared memory by their
-//   minimum-image displacements (d - ceil(d - 0.5) against the wrapped reference), vectorised,
-//   once per element and off the MMA critical path;
-// * MMA: DMMA m8n8k4 (the FP64 tensor path on sm_100; tcgen05 has no f64 kind) with register
-//   double-buffered A/B fragments, accumulators in registers;
-// * epilogue (once per DOF tile): the amplitude tile goes to shared memory and is re-read with a
-//   frame-per-thread mapping, so that all lanes of a warp evaluate the SAME DOF at a time: the
-//   piecewise-polynomial table loads are warp-uniform (one broadcast transaction), Horner runs in
-//   registers and each thread owns its frame's 3x3 partial sum (no shuffles).  The (S,J)
-//   amplitude matrix never touches HBM.
+// One persistent CTA per SM.  A work tile is 128 frames x all dense DOFs; DOFs are walked in tiles
+// of 64, K = 3N in chunks of 16 through a 4-stage cp.async ring.  The kernel is warp-specialised:
+//   warps 8-11 (producers): fill the ring with cp.async, then replace the raw fractional positions
+//       of a landed chunk in shared memory by their minimum-image displacements
+//       (d - ceil(d - 0.5) against the wrapped reference; vectorised, once per element);
+//   warps 0-7 (MMA): LDS + DMMA m8n8k4 only (the FP64 tensor path on sm_100; tcgen05 has no f64
+//       kind), register double-buffered fragments, 16x64 accumulator tile per warp; two MMA warps
+//       per scheduler so that one covers the other's LDS / mbarrier bubbles (the DMMA issue queue
+//       is shallow: tools/dmma_occupancy.cu, tools/dmma_operands.cu).
+//   Stages are handed over with mbarriers (full/empty), so MMA warps never wait on each other.
+// Epilogue (once per DOF tile), chained DMMA: the amplitude accumulators are turned, in registers,
+// into truncated-power features ((x-x0)^m, max(x-b,0)^m) and fed as the A operand of a second DMMA
+// against the per-DOF coefficient table, accumulating the frame's 3x3 tensor directly — no shared
+// memory round trip, no per-frame table walk; the (S,J) amplitude matrix never touches HBM.
 // FP64-pipe bound: 2*3N*J flops per frame against the measured DMMA rate (profiles/fp64_peaks.json).
 #include <algorithm>
 
@@ -29,221 +30,9 @@ constexpr int kRS2 = 20;      // padded smem row stride (doubles): conflict-free
 constexpr int kStages2 = 4;
 constexpr int kAmpStride = 65;  // doubles per frame row of the amplitude tile
 
-// WN = warps along the DOF axis (1: 128-frame tiles, warp tile 16x64; 2: 64-frame tiles, 16x32)
-template <int DEG, int PB, int WN, bool WRAP, bool ALIGN16>
-__global__ void __launch_bounds__(256, 1)
-    dense_kernel_v2(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ V,
-                    const int32_t* __restrict__ piece_off, const double* __restrict__ breaks,
-                    const double* __restrict__ pieces, int64_t num_frames, int K, int Kv, int Jpad, int accumulate,
-                    Alpha0 a0, double* __restrict__ alpha) {
-    constexpr int WM = 8 / WN;          // warps along the frame axis
-    constexpr int FT = 16 * WM;         // frames per tile
-    constexpr int NT = 8 / WN;          // 8-wide DOF sub-tiles per warp
-    constexpr int JW = kJT2 / WN;       // DOFs per warp
-    constexpr int GROUPS = 256 / FT;    // epilogue: thread groups sharing a frame
-    constexpr int JG = kJT2 / GROUPS;   // DOFs per epilogue thread per J tile
-    constexpr int REC = 1 + 9 * (DEG + 1);
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* As = reinterpret_cast<double*>(smem_raw);          // [kStages2][FT][kRS2]
-    double* Bs = As + (size_t)kStages2 * FT * kRS2;            // [kStages2][kJT2][kRS2]
-    double* amp = Bs + (size_t)kStages2 * kJT2 * kRS2;         // [FT][kAmpStride]
-    double* comb = amp + (size_t)FT * kAmpStride;              // [GROUPS][FT][9]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int wm = warp % WM, wn = warp / WM;
-    const int chunks = Kv / kKC2;
-    const int jtiles = Jpad / kJT2;
-    const int64_t total = (int64_t)jtiles * chunks;
-    const int64_t num_tiles = (num_frames + FT - 1) / FT;
-    // epilogue mapping: consecutive lanes = consecutive frames, a whole warp shares its DOF group
-    const int ef = threadIdx.x % FT, eg = threadIdx.x / FT;
-
-    // per-thread constants of the cp.async / wrap work split (row and 16-byte segment are fixed)
-    constexpr int A_ITEMS = ALIGN16 ? (FT * 8) / 256 : (FT * 16) / 256;
-    constexpr int A_SEGS = ALIGN16 ? 8 : 16;           // copy items per row
-    constexpr int A_ELEMS = ALIGN16 ? 2 : 1;           // doubles per copy item
-    constexpr int A_ROWSTEP = 256 / A_SEGS;            // rows between a thread's items
-    const int a_row0 = threadIdx.x / A_SEGS, a_seg = threadIdx.x % A_SEGS;
-    const int b_row0 = threadIdx.x >> 3, b_seg = threadIdx.x & 7;
-    const uint32_t as_base = smem_u32(As), bs_base = smem_u32(Bs);
-    constexpr uint32_t A_STAGE_BYTES = FT * kRS2 * 8, B_STAGE_BYTES = kJT2 * kRS2 * 8;
-    const uint32_t a_dst0 = as_base + (uint32_t)(a_row0 * kRS2 + a_seg * A_ELEMS) * 8u;
-    const uint32_t b_dst0 = bs_base + (uint32_t)(b_row0 * kRS2 + b_seg * 2) * 8u;
-    const double* v_src0 = V + (int64_t)b_row0 * Kv + b_seg * 2;
-    const int w_row0 = threadIdx.x >> 3, w_seg = threadIdx.x & 7;  // wrap pass: double2 items
-
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t frame0 = tile * FT;
-        // source row pointers of this tile (nullptr for rows past the end: zero-filled)
-        const double* a_src_row[A_ITEMS];
-#pragma unroll
-        for (int r = 0; r < A_ITEMS; r++) {
-            const int64_t frame = frame0 + a_row0 + r * A_ROWSTEP;
-            a_src_row[r] = (frame < num_frames) ? in + frame * (int64_t)K + a_seg * A_ELEMS : nullptr;
-        }
-        // pipeline cursors (no 64-bit division in the loop): chunk index / DOF tile / ring stage
-        int is_kc = 0, is_jt = 0, is_st = 0;  // next chunk to issue
-        auto issue = [&]() {
-            if (is_jt < jtiles) {
-                const int col = is_kc * kKC2 + a_seg * A_ELEMS;
-                const int rem = K - col;  // doubles left in the row from this item's first column
-                const int bytes = ALIGN16 ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : (rem >= 1 ? 8 : 0);
-                const uint32_t a_dst = a_dst0 + (uint32_t)is_st * A_STAGE_BYTES;
-#pragma unroll
-                for (int r = 0; r < A_ITEMS; r++) {
-                    const double* row = a_src_row[r];
-                    const int nb = row ? bytes : 0;
-                    const double* src = nb ? row + is_kc * kKC2 : in;
-                    if (ALIGN16) cp_async_16(a_dst + (uint32_t)(r * A_ROWSTEP * kRS2) * 8u, src, nb);
-                    else cp_async_8(a_dst + (uint32_t)(r * A_ROWSTEP * kRS2) * 8u, src, nb);
-                }
-                const uint32_t b_dst = b_dst0 + (uint32_t)is_st * B_STAGE_BYTES;
-                const double* vsrc = v_src0 + ((int64_t)is_jt * kJT2) * Kv + is_kc * kKC2;
-#pragma unroll
-                for (int r = 0; r < (kJT2 * 8) / 256; r++)
-                    cp_async_16(b_dst + (uint32_t)(r * 32 * kRS2) * 8u, vsrc + (int64_t)r * 32 * Kv, 16);
-                if (++is_kc == chunks) {
-                    is_kc = 0;
-                    ++is_jt;
-                }
-                is_st = (is_st + 1) & (kStages2 - 1);
-            }
-            cp_async_commit();
-        };
-        // raw positions of a landed chunk -> minimum-image fractional displacements, in place
-        int wr_kc = 0, wr_st = 0;
-        int64_t wr_left = total;
-        auto wrap_chunk = [&]() {
-            if (!WRAP) return;
-            if (wr_left > 0) {
-                double* a = As + (size_t)wr_st * FT * kRS2 + w_row0 * kRS2 + w_seg * 2;
-                const double2 rf = __ldg(reinterpret_cast<const double2*>(ref + wr_kc * kKC2 + w_seg * 2));
-#pragma unroll
-                for (int r = 0; r < FT / 32; r++) {
-                    double2* p = reinterpret_cast<double2*>(a + r * 32 * kRS2);
-                    double2 v = *p;
-                    v.x = wrap_disp(v.x, rf.x);
-                    v.y = wrap_disp(v.y, rf.y);
-                    *p = v;
-                }
-                --wr_left;
-                if (++wr_kc == chunks) wr_kc = 0;
-                wr_st = (wr_st + 1) & (kStages2 - 1);
-            }
-        };
-
-        double out9[9];
-#pragma unroll
-        for (int q = 0; q < 9; q++) out9[q] = 0.0;
-        double acc[2][NT][2];
-
-        __syncthreads();  // the previous tile's smem reads are finished
-        for (int p = 0; p < kStages2 - 1; p++) issue();
-        cp_async_wait<kStages2 - 2>();
-        __syncthreads();
-        wrap_chunk();
-
-        int kc = 0, jt = 0, st = 0;
-        for (int64_t it = 0; it < total; it++) {
-            if (kc == 0) {
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-            }
-            cp_async_wait<1>();  // chunk it+1 has landed (this thread's copies)
-            __syncthreads();     // ... everyone's; MMA(it-1) done; wrap(it) visible
-            issue();
-            wrap_chunk();
-
-            const double* a_src = As + (size_t)st * FT * kRS2 + (wm * 16 + g) * kRS2 + t;
-            const double* b_src = Bs + (size_t)st * kJT2 * kRS2 + (wn * JW + g) * kRS2 + t;
-            double af[2][2], bf[2][NT];
-            af[0][0] = a_src[0];
-            af[0][1] = a_src[8 * kRS2];
-#pragma unroll
-            for (int nt = 0; nt < NT; nt++) bf[0][nt] = b_src[nt * 8 * kRS2];
-#pragma unroll
-            for (int s = 0; s < kKC2 / 4; s++) {
-                const int cur = s & 1, nxt = cur ^ 1;
-                if (s + 1 < kKC2 / 4) {  // fragments of the next k-step while this one's DMMAs issue
-                    af[nxt][0] = a_src[4 * (s + 1)];
-                    af[nxt][1] = a_src[8 * kRS2 + 4 * (s + 1)];
-#pragma unroll
-                    for (int nt = 0; nt < NT; nt++) bf[nxt][nt] = b_src[nt * 8 * kRS2 + 4 * (s + 1)];
-                }
-#pragma unroll
-                for (int nt = 0; nt < NT; nt++) {
-                    dmma884(acc[0][nt][0], acc[0][nt][1], af[cur][0], bf[cur][nt]);
-                    dmma884(acc[1][nt][0], acc[1][nt][1], af[cur][1], bf[cur][nt]);
-                }
-            }
-            const bool last_chunk = (kc == chunks - 1);
-            const int jt_now = jt;
-            if (++kc == chunks) {
-                kc = 0;
-                ++jt;
-            }
-            st = (st + 1) & (kStages2 - 1);
-
-            if (last_chunk) {
-                // ---- epilogue of this DOF tile ----
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < NT; nt++) {
-                        double* dst = amp + (size_t)(wm * 16 + mt * 8 + g) * kAmpStride + wn * JW + nt * 8 + 2 * t;
-                        dst[0] = acc[mt][nt][0];
-                        dst[1] = acc[mt][nt][1];
-                    }
-                __syncthreads();
-                const double* arow = amp + (size_t)ef * kAmpStride + eg * JG;
-                const int j0 = jt_now * kJT2 + eg * JG;
-#pragma unroll 2
-                for (int jj = 0; jj < JG; jj++) {
-                    const double x = arow[jj];
-                    const int p0 = __ldg(piece_off + j0 + jj);  // warp-uniform
-                    int p = 0;
-                    if (PB > 0) {
-                        const int np = __ldg(piece_off + j0 + jj + 1) - p0;
-#pragma unroll
-                        for (int b = 0; b < PB; b++)
-                            if (b + 1 < np) p += (x >= __ldg(breaks + p0 + b)) ? 1 : 0;
-                    }
-                    const double* rec = pieces + (int64_t)(p0 + p) * REC;
-                    const double dx = x - __ldg(rec);
-#pragma unroll
-                    for (int q = 0; q < 9; q++) {
-                        double r = __ldg(rec + 1 + q);
-#pragma unroll
-                        for (int mm = 1; mm <= DEG; mm++) r = fma(r, dx, __ldg(rec + 1 + 9 * mm + q));
-                        out9[q] += r;
-                    }
-                }
-                // the next amplitude dump is a whole K loop (>= 1 barrier) away: no barrier needed here
-            }
-        }
-        cp_async_wait<0>();
-
-        // ---- combine the GROUPS partial sums of every frame and store (coalesced) ----
-#pragma unroll
-        for (int q = 0; q < 9; q++) comb[((size_t)eg * FT + ef) * 9 + q] = out9[q];
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < FT * 9; idx += 256) {
-            const int f = idx / 9, q = idx % 9;
-            const int64_t frame = frame0 + f;
-            if (frame < num_frames) {
-                double sum = 0.0;
-#pragma unroll
-                for (int grp = 0; grp < GROUPS; grp++) sum += comb[((size_t)grp * FT + f) * 9 + q];
-                const double base = accumulate ? alpha[frame * 9 + q] : a0.v[q];
-                alpha[frame * 9 + q] = sum + base;
-            }
-        }
-    }
-}
+// A/B hook (rn_debug_set_dense_config): generation 1 = rn_polarizability.cu, 3 = warp-specialised with
+// the piecewise-polynomial epilogue, 4 = warp-specialised with the chained-DMMA epilogue (default)
+static int g_dense_version = 4;
 
 // ------------------------------------------------------------------------------------
 // Third generation: warp-specialised.  Warps 0-3 only issue LDS + DMMA (one MMA warp per
@@ -489,12 +278,14 @@ __global__ void __launch_bounds__(256, 1)
 // holds amplitudes of frame g for DOFs 2t and 2t+1).  No shared-memory round trip, no per-frame
 // table walks: one coefficient fragment is shared by 32 frames of the warp.
 template <int DEG, int NBK, bool FULL, bool WRAP, bool ALIGN16>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
     dense_kernel_tp(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ V,
                     const double* __restrict__ tp_x0, const double* __restrict__ tp_brk,
                     const double* __restrict__ tp_c8, const double* __restrict__ tp_c9, int64_t num_frames, int K, int Kv, int Jpad, int accumulate,
                     Alpha0 a0, double* __restrict__ alpha) {
-    constexpr int FT = 128;  // frames per tile: 4 MMA warps x 32
+    constexpr int FT = 128;    // frames per tile: 8 MMA warps x 16
+    constexpr int MMAW = 8;    // MMA warps (two per scheduler: one covers the other's LDS / barrier bubbles)
+    constexpr int MTW = 2;     // 8-frame groups per MMA warp
     constexpr int PERB = FULL ? DEG + 1 : 1;  // features per break slot
     constexpr int NF = DEG + NBK * PERB;      // features per DOF
     constexpr int NBS = NBK > 0 ? NBK : 1;    // stride of the break table
@@ -513,15 +304,15 @@ __global__ void __launch_bounds__(256, 1)
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages2; s++) {
             mbar_init2(full0 + 8 * s, 128);  // every producer thread arrives after its wrap items
-            mbar_init2(empty0 + 8 * s, 4);   // one arrival per MMA warp
+            mbar_init2(empty0 + 8 * s, MMAW);  // one arrival per MMA warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp >= 4) {
+    if (warp >= MMAW) {
         // =========================== producers (128 threads) ===========================
-        const int ptid = threadIdx.x - 128;
+        const int ptid = threadIdx.x - MMAW * 32;
         constexpr int A_SEGS = ALIGN16 ? 8 : 16;
         constexpr int A_ELEMS = ALIGN16 ? 2 : 1;
         constexpr int A_ITEMS = (FT * A_SEGS) / 128;
@@ -577,14 +368,21 @@ __global__ void __launch_bounds__(256, 1)
             issue();
             issue();
             int wr_kc = 0;
+            // reference positions of the chunk to wrap: fetched one iteration ahead (off the critical path)
+            double2 rf_next = make_double2(0.0, 0.0);
+            if (WRAP) rf_next = __ldg(reinterpret_cast<const double2*>(ref + w_seg * 2));
             for (int64_t c = 0; c < total; c++) {
+                const double2 rf = rf_next;
+                if (WRAP) {
+                    const int nkc = (wr_kc + 1 == chunks) ? 0 : wr_kc + 1;
+                    rf_next = __ldg(reinterpret_cast<const double2*>(ref + nkc * kKC2 + w_seg * 2));
+                }
                 issue();             // chunk c+2
                 cp_async_wait<2>();  // this thread's copies of chunk c have landed
                 asm volatile("bar.sync 1, 128;" ::: "memory");  // ... and every producer's
                 const uint32_t st = wrapped & (kStages2 - 1);
                 if (WRAP) {
                     double* a = As + (size_t)st * FT * kRS2 + w_row0 * kRS2 + w_seg * 2;
-                    const double2 rf = __ldg(reinterpret_cast<const double2*>(ref + wr_kc * kKC2 + w_seg * 2));
 #pragma unroll
                     for (int r = 0; r < FT / 16; r++) {
                         double2* p = reinterpret_cast<double2*>(a + r * 16 * kRS2);
@@ -605,29 +403,29 @@ __global__ void __launch_bounds__(256, 1)
 
     // =============================== MMA warps (128 threads) ===============================
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp;  // frames 32*wm .. 32*wm+31
+    const int wm = warp;  // frames 16*wm .. 16*wm+15
     uint32_t consumed = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t frame0 = tile * FT;
-        double out[4][2], o9[4];
+        double out[MTW][2], o9[MTW];
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++) out[mt][0] = out[mt][1] = o9[mt] = 0.0;
-        double acc[4][8][2];
+        for (int mt = 0; mt < MTW; mt++) out[mt][0] = out[mt][1] = o9[mt] = 0.0;
+        double acc[MTW][8][2];
         int kc = 0, jt = 0;
         for (int64_t c = 0; c < total; c++) {
             if (kc == 0) {
 #pragma unroll
-                for (int mt = 0; mt < 4; mt++)
+                for (int mt = 0; mt < MTW; mt++)
 #pragma unroll
                     for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
             }
             const uint32_t st = consumed & (kStages2 - 1);
             mbar_wait2(full0 + 8 * st, (consumed >> 2) & 1);
-            const double* a_src = As + (size_t)st * FT * kRS2 + (wm * 32 + g) * kRS2 + t;
+            const double* a_src = As + (size_t)st * FT * kRS2 + (wm * 8 * MTW + g) * kRS2 + t;
             const double* b_src = Bs + (size_t)st * kJT2 * kRS2 + g * kRS2 + t;
-            double af[2][4], bf[2][8];
+            double af[2][MTW], bf[2][8];
 #pragma unroll
-            for (int mt = 0; mt < 4; mt++) af[0][mt] = a_src[mt * 8 * kRS2];
+            for (int mt = 0; mt < MTW; mt++) af[0][mt] = a_src[mt * 8 * kRS2];
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) bf[0][nt] = b_src[nt * 8 * kRS2];
 #pragma unroll
@@ -635,14 +433,14 @@ __global__ void __launch_bounds__(256, 1)
                 const int cur = s & 1, nxt = cur ^ 1;
                 if (s + 1 < kKC2 / 4) {
 #pragma unroll
-                    for (int mt = 0; mt < 4; mt++) af[nxt][mt] = a_src[mt * 8 * kRS2 + 4 * (s + 1)];
+                    for (int mt = 0; mt < MTW; mt++) af[nxt][mt] = a_src[mt * 8 * kRS2 + 4 * (s + 1)];
 #pragma unroll
                     for (int nt = 0; nt < 8; nt++) bf[nxt][nt] = b_src[nt * 8 * kRS2 + 4 * (s + 1)];
                 }
 #pragma unroll
                 for (int nt = 0; nt < 8; nt++)
 #pragma unroll
-                    for (int mt = 0; mt < 4; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[cur][mt], bf[cur][nt]);
+                    for (int mt = 0; mt < MTW; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[cur][mt], bf[cur][nt]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive2(empty0 + 8 * st);  // stage may be refilled
@@ -674,7 +472,7 @@ __global__ void __launch_bounds__(256, 1)
                             c9[f] = __ldg(tp_c9 + (int64_t)jl * NF + f);
                         }
 #pragma unroll
-                        for (int mt = 0; mt < 4; mt++) {
+                        for (int mt = 0; mt < MTW; mt++) {
                             const double x = acc[mt][nt][c];
                             const double u = x - x0;
                             double pw = u;
@@ -713,11 +511,11 @@ __global__ void __launch_bounds__(256, 1)
         }
         // ---- store: lane (g,t) holds components 2t, 2t+1 of frames 8*mt+g; component 8 is summed over t ----
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++) {
+        for (int mt = 0; mt < MTW; mt++) {
             double v9 = o9[mt];
             v9 += __shfl_xor_sync(0xffffffffu, v9, 1);
             v9 += __shfl_xor_sync(0xffffffffu, v9, 2);
-            const int64_t frame = frame0 + wm * 32 + mt * 8 + g;
+            const int64_t frame = frame0 + wm * 8 * MTW + mt * 8 + g;
             if (frame < num_frames) {
                 double* dst = alpha + frame * 9;
                 // a0 holds what must be added on top of the running value (see launch_tp_cfg)
@@ -749,7 +547,7 @@ static int launch_tp_cfg(const rn_model* m, const double* d_in, bool wrap, bool 
     {                                                                                                        \
         auto kern = dense_kernel_tp<DEG, NBK, FULL, W, A>;                                                   \
         RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-        kern<<<grid, 256, smem, stream>>>(d_in, m->d_ref_wrapped, V, m->d_tp_x0, m->d_tp_brk, m->d_tp_c8,   \
+        kern<<<grid, 384, smem, stream>>>(d_in, m->d_ref_wrapped, V, m->d_tp_x0, m->d_tp_brk, m->d_tp_c8,   \
                                           m->d_tp_c9, num_frames, K, (int)m->v_cols, (int)m->dense_pad,      \
                                           accumulate ? 1 : 0, a0, d_alpha);                                  \
     }
@@ -823,69 +621,6 @@ static int launch_v3_deg(const rn_model* m, const double* d_in, bool wrap, bool 
     return 1;
 }
 
-template <int DEG, int PB, int WN>
-static int launch_v2_cfg(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
-                         double* d_alpha, cudaStream_t stream) {
-    Alpha0 a0;
-    for (int q = 0; q < 9; q++) a0.v[q] = m->alpha0[q];
-    const int K = (int)m->dim;
-    constexpr int FT = 16 * (8 / WN);
-    constexpr int GROUPS = 256 / FT;
-    const bool align16 = (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (K % 2 == 0);
-    const size_t smem = ((size_t)kStages2 * (FT + kJT2) * kRS2 + (size_t)FT * kAmpStride + (size_t)GROUPS * FT * 9) *
-                        sizeof(double);
-    const int64_t tiles = (num_frames + FT - 1) / FT;
-    const int grid = (int)std::min<int64_t>(tiles, m->sm_count);
-    const double* V = wrap ? m->d_v_frac : m->d_v_cart;
-#define RN_V2_LAUNCH(W, A)                                                                                     \
-    {                                                                                                          \
-        auto kern = dense_kernel_v2<DEG, PB, WN, W, A>;                                                        \
-        RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-        kern<<<grid, 256, smem, stream>>>(d_in, m->d_ref_wrapped, V, m->d_piece_off, m->d_breaks, m->d_pieces, \
-                                          num_frames, K, (int)m->v_cols, (int)m->dense_pad, accumulate ? 1 : 0, a0, \
-                                          d_alpha);                                                            \
-    }
-    if (wrap) {
-        if (align16) RN_V2_LAUNCH(true, true) else RN_V2_LAUNCH(true, false)
-    } else {
-        if (align16) RN_V2_LAUNCH(false, true) else RN_V2_LAUNCH(false, false)
-    }
-#undef RN_V2_LAUNCH
-    RN_LAUNCHED();
-    RN_CUDA(cudaGetLastError());
-    return RN_OK;
-}
-
-static int g_dense_version = 4;  // 1, 2, 3 = earlier generations (A/B testing); 4 = warp-specialised + chained-DMMA epilogue  // 1 = first-generation kernel (rn_polarizability.cu), 2 = this file
-static int g_dense_wn = 0;       // 0 = automatic
-
-template <int DEG, int PB>
-static int launch_v2_tile(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
-                          double* d_alpha, cudaStream_t stream) {
-    // 128-frame tiles reuse B fragments twice as often; 64-frame tiles halve the wave-quantisation
-    // loss of the persistent grid when there are few tiles per SM.
-    int wn = g_dense_wn;
-    if (wn == 0) {
-        const int64_t tiles128 = (num_frames + 127) / 128;
-        const int64_t waves = (tiles128 + m->sm_count - 1) / m->sm_count;
-        const double eff128 = (double)tiles128 / (double)(waves * m->sm_count);
-        wn = (eff128 < 0.93) ? 2 : 1;
-    }
-    if (wn == 2) return launch_v2_cfg<DEG, PB, 2>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
-    return launch_v2_cfg<DEG, PB, 1>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
-}
-
-template <int DEG>
-static int launch_v2_deg(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
-                         double* d_alpha, cudaStream_t stream) {
-    const int pb = m->dense_max_pieces - 1;  // interior breaks to scan
-    if (pb <= 0) return launch_v2_tile<DEG, 0>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
-    if (pb <= 1) return launch_v2_tile<DEG, 1>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
-    if (pb <= 3) return launch_v2_tile<DEG, 3>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
-    if (pb <= 8) return launch_v2_tile<DEG, 8>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
-    return 1;  // more pieces than the unrolled search covers: use the first-generation kernel
-}
-
 int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
                  double* d_alpha, cudaStream_t stream) {
     if (num_frames == 0) return RN_OK;
@@ -907,15 +642,6 @@ int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumula
             default: break;
         }
     }
-    if (rc == 1 && g_dense_version >= 2) {
-        switch (m->dense_degree) {
-            case 0:
-            case 1: rc = launch_v2_deg<1>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream); break;
-            case 2: rc = launch_v2_deg<2>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream); break;
-            case 3: rc = launch_v2_deg<3>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream); break;
-            default: break;  // degrees 4, 5: first-generation kernel
-        }
-    }
     if (rc == 1) rc = launch_dense_v1(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
     return rc;
 }
@@ -923,7 +649,7 @@ int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumula
 }  // namespace rn
 
 // Test / tuning hooks (not in the public header).
-extern "C" void rn_debug_set_dense_config(int version, int wn) {
+extern "C" void rn_debug_set_dense_config(int version, int unused) {
+    (void)unused;
     rn::g_dense_version = version;
-    rn::g_dense_wn = wn;
 }

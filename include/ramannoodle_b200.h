@@ -99,6 +99,19 @@ int rn_calc_polarizabilities_host(const rn_model* model, const double* h_positio
                                   int64_t num_frames, double* h_alpha, double* d_alpha,
                                   int64_t chunk_frames);
 
+/* Multi-destination forms for frame-sharded multi-GPU runs: the evaluated rows are stored to
+ * every pointer of d_alpha_outputs (num_outputs in 1..8).  outputs[0] is the local series, the
+ * others are the same buffer on peer GPUs (peer-mapped device memory, e.g. symmetric memory over
+ * NVLink); all pointers are pre-offset to this rank's first frame.  The hot kernels write the
+ * peers' rows themselves (ld/st.global on mapped peer pointers): the all-gather of the
+ * (S,3,3) series is fused into the evaluation.  The caller synchronises the ranks afterwards. */
+int rn_calc_polarizabilities_multi(const rn_model* model, const double* d_positions,
+                                   int64_t num_frames, double* const* d_alpha_outputs,
+                                   int num_outputs, void* stream);
+int rn_calc_polarizabilities_host_multi(const rn_model* model, const double* h_positions,
+                                        int64_t num_frames, double* const* d_alpha_outputs,
+                                        int num_outputs, int64_t chunk_frames);
+
 /* Trajectory.__init__ stores apply_pbc(positions_ts) (dynamics/_trajectory.py:45;
  * structure/utils.py:27: p - p // 1).  Elementwise, in place allowed (d_out == d_in). */
 int rn_apply_pbc(const double* d_in, double* d_out, int64_t count, void* stream);
@@ -119,6 +132,18 @@ int64_t rn_spectrum_num_points(int64_t num_frames);
 int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, double timestep_fs,
                    int laser_correction, double laser_wavelength_nm, int bose_einstein_correction,
                    double temperature_K, double* d_wavenumbers, double* d_intensities, void* stream);
+/* Sharded form of rn_md_spectrum for multi-GPU runs (one process per GPU).  The orientational
+ * average of _raman.py:286-297 is a sum of three independent packed transforms ("parts": 0 =
+ * anisotropy differences, 1 = trace + xy, 2 = yz + xz); rn_md_spectrum_part writes the
+ * uncorrected contribution of one part to d_partial (P,), parts from different ranks are summed
+ * (all-reduce), and rn_md_spectrum_finish turns the sum into (wavenumbers, intensities) with the
+ * optional corrections.  part 0 + part 1 + part 2 followed by finish == rn_md_spectrum. */
+int rn_md_spectrum_part(rn_spectrum_plan* plan, const double* d_alpha, int part, double* d_partial,
+                        void* stream);
+int rn_md_spectrum_finish(int64_t num_frames, const double* d_partial_sum, double timestep_fs,
+                          int laser_correction, double laser_wavelength_nm,
+                          int bose_einstein_correction, double temperature_K, double* d_wavenumbers,
+                          double* d_intensities, void* stream);
 /* calc_signal_spectrum(signal, sampling_rate) (spectrum/utils.py:95-124) for one real signal of
  * length M = S-1 of the plan: outputs ceil(M/2) points (bin 0 included). */
 int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal, double sampling_rate,

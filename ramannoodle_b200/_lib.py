@@ -36,6 +36,10 @@ PROTOTYPES = {
                                              ctypes.c_void_p, ctypes.c_void_p]),
     "rn_calc_polarizabilities_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "rn_calc_polarizabilities_multi": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                      ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "rn_calc_polarizabilities_host_multi": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int64]),
     "rn_apply_pbc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "rn_spectrum_plan_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "rn_spectrum_plan_destroy": (ctypes.c_int, [ctypes.c_void_p]),
@@ -43,6 +47,11 @@ PROTOTYPES = {
     "rn_md_spectrum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
                                       ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p]),
+    "rn_md_spectrum_part": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_void_p]),
+    "rn_md_spectrum_finish": (ctypes.c_int, [ctypes.c_int64, ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
+                                             ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]),
     "rn_signal_spectrum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p]),
     "rn_convolve_workspace_size": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int64]),

@@ -98,11 +98,20 @@ struct rn_model {
 
 namespace rn {
 
-// kernels / launchers implemented in rn_polarizability.cu
+// Extra destinations of the polarizability series: the same rows are stored to every pointer
+// (peer GPUs' buffers mapped over NVLink) by the kernel itself — the all-gather is fused into the
+// evaluation.  Pointers are pre-offset to this rank's first frame.
+struct AlphaPeers {
+    double* ptr[7];
+    int count;
+};
+
+// kernels / launchers implemented in rn_polarizability.cu / rn_dense.cu.  `peers` may be null;
+// *peers_done is set when the launched kernel stored to the peers itself.
 int launch_affine(const rn_model* m, const double* d_in, bool wrap, int64_t num_frames, double* d_alpha,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const AlphaPeers* peers = nullptr, bool* peers_done = nullptr);
 int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
-                 double* d_alpha, cudaStream_t stream);
+                 double* d_alpha, cudaStream_t stream, const AlphaPeers* peers = nullptr, bool* peers_done = nullptr);
 int launch_dense_v1(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
                     double* d_alpha, cudaStream_t stream);
 int launch_fill_alpha0(const rn_model* m, int64_t num_frames, double* d_alpha, cudaStream_t stream);

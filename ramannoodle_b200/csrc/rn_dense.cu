@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(384, 1)
     dense_kernel_tp(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ V,
                     const double* __restrict__ tp_x0, const double* __restrict__ tp_brk,
                     const double* __restrict__ tp_c8, const double* __restrict__ tp_c9, int64_t num_frames, int K, int Kv, int Jpad, int accumulate,
-                    Alpha0 a0, double* __restrict__ alpha) {
+                    Alpha0 a0, double* __restrict__ alpha, AlphaPeers peers) {
     constexpr int FT = 128;    // frames per tile: 8 MMA warps x 16
     constexpr int MMAW = 8;    // MMA warps (two per scheduler: one covers the other's LDS / barrier bubbles)
     constexpr int MTW = 2;     // 8-frame groups per MMA warp
@@ -521,9 +521,18 @@ __global__ void __launch_bounds__(384, 1)
                 // a0 holds what must be added on top of the running value (see launch_tp_cfg)
                 const double b0 = (accumulate ? dst[2 * t] : 0.0) + a0.v[2 * t];
                 const double b1 = (accumulate ? dst[2 * t + 1] : 0.0) + a0.v[2 * t + 1];
-                dst[2 * t] = out[mt][0] + b0;
-                dst[2 * t + 1] = out[mt][1] + b1;
-                if (t == 0) dst[8] = v9 + ((accumulate ? dst[8] : 0.0) + a0.v[8]);
+                const double r0 = out[mt][0] + b0, r1 = out[mt][1] + b1;
+                const double r8 = v9 + ((accumulate ? dst[8] : 0.0) + a0.v[8]);
+                dst[2 * t] = r0;
+                dst[2 * t + 1] = r1;
+                if (t == 0) dst[8] = r8;
+                // fused all-gather: the same row goes to every peer GPU's series over NVLink
+                for (int p = 0; p < peers.count; p++) {
+                    double* pd = peers.ptr[p] + frame * 9;
+                    pd[2 * t] = r0;
+                    pd[2 * t + 1] = r1;
+                    if (t == 0) pd[8] = r8;
+                }
             }
         }
     }
@@ -531,7 +540,7 @@ __global__ void __launch_bounds__(384, 1)
 
 template <int DEG, int NBK, bool FULL>
 static int launch_tp_cfg(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
-                         double* d_alpha, cudaStream_t stream) {
+                         double* d_alpha, cudaStream_t stream, const AlphaPeers& peers) {
     // constants: alpha0_tp = alpha0 + sum of the dense DOFs' constant terms.  When the affine kernel
     // already wrote alpha0 + D.G (accumulate), only the dense constants remain to be added.
     Alpha0 a0;
@@ -549,7 +558,7 @@ static int launch_tp_cfg(const rn_model* m, const double* d_in, bool wrap, bool 
         RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
         kern<<<grid, 384, smem, stream>>>(d_in, m->d_ref_wrapped, V, m->d_tp_x0, m->d_tp_brk, m->d_tp_c8,   \
                                           m->d_tp_c9, num_frames, K, (int)m->v_cols, (int)m->dense_pad,      \
-                                          accumulate ? 1 : 0, a0, d_alpha);                                  \
+                                          accumulate ? 1 : 0, a0, d_alpha, peers);                           \
     }
     if (wrap) {
         if (align16) RN_TP_LAUNCH(true, true) else RN_TP_LAUNCH(true, false)
@@ -564,18 +573,18 @@ static int launch_tp_cfg(const rn_model* m, const double* d_in, bool wrap, bool 
 
 template <int DEG>
 static int launch_tp_deg(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
-                         double* d_alpha, cudaStream_t stream) {
+                         double* d_alpha, cudaStream_t stream, const AlphaPeers& peers) {
     const bool full = m->tp_mode == 2;
     switch (m->tp_breaks) {
-        case 0: return launch_tp_cfg<DEG, 0, false>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
+        case 0: return launch_tp_cfg<DEG, 0, false>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, peers);
         case 1:
-            return full ? launch_tp_cfg<DEG, 1, true>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream)
-                        : launch_tp_cfg<DEG, 1, false>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
+            return full ? launch_tp_cfg<DEG, 1, true>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, peers)
+                        : launch_tp_cfg<DEG, 1, false>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, peers);
         case 2:
-            return full ? launch_tp_cfg<DEG, 2, true>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream)
-                        : launch_tp_cfg<DEG, 2, false>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
+            return full ? launch_tp_cfg<DEG, 2, true>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, peers)
+                        : launch_tp_cfg<DEG, 2, false>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, peers);
         case 3:
-            return full ? 1 : launch_tp_cfg<DEG, 3, false>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream);
+            return full ? 1 : launch_tp_cfg<DEG, 3, false>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, peers);
         default: return 1;
     }
 }
@@ -622,16 +631,21 @@ static int launch_v3_deg(const rn_model* m, const double* d_in, bool wrap, bool 
 }
 
 int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
-                 double* d_alpha, cudaStream_t stream) {
+                 double* d_alpha, cudaStream_t stream, const AlphaPeers* peers, bool* peers_done) {
     if (num_frames == 0) return RN_OK;
     int rc = 1;
+    AlphaPeers fused;
+    fused.count = 0;
+    if (peers) fused = *peers;
+    if (peers_done) *peers_done = false;
     if (g_dense_version == 4 && m->tp_mode != 0 && m->tp_features <= 12) {
         switch (m->dense_degree) {
-            case 1: rc = launch_tp_deg<1>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream); break;
-            case 2: rc = launch_tp_deg<2>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream); break;
-            case 3: rc = launch_tp_deg<3>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream); break;
+            case 1: rc = launch_tp_deg<1>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, fused); break;
+            case 2: rc = launch_tp_deg<2>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, fused); break;
+            case 3: rc = launch_tp_deg<3>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, fused); break;
             default: break;
         }
+        if (rc == RN_OK && peers_done) *peers_done = true;  // the chained kernel stores to the peers itself
     }
     if (rc == 1 && g_dense_version >= 3) {
         switch (m->dense_degree) {

@@ -120,7 +120,7 @@ template <int KP, int MT, int STAGES, bool WRAP>
 __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 1)
     affine_tma_kernel(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ G,
                       int64_t num_frames, int K, int row_stride, int stage_doubles, Alpha0 a0,
-                      double* __restrict__ alpha) {
+                      double* __restrict__ alpha, AlphaPeers peers) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ROWS = 8 * MT;
     constexpr int RED = kAffineWarps * ROWS * kRedStride;  // doubles per reduction buffer
@@ -244,7 +244,12 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
 #pragma unroll
             for (int w = 0; w < kAffineWarps; w++) sum += r[(size_t)w * ROWS * kRedStride];
             const int64_t frame = tile * ROWS + f;
-            if (frame < num_frames) alpha[frame * 9 + q] = sum + a0.v[q];
+            if (frame < num_frames) {
+                const double value = sum + a0.v[q];
+                alpha[frame * 9 + q] = value;
+                // fused all-gather: the same row goes to every peer GPU's series over NVLink
+                for (int p = 0; p < peers.count; p++) peers.ptr[p][frame * 9 + q] = value;
+            }
         }
     }
 }
@@ -253,7 +258,7 @@ static int g_affine_mt = 0;  // 0 = automatic
 
 template <int KP, int MT, int STAGES, bool WRAP>
 static int launch_affine_tma_cfg(const rn_model* m, const double* d_in, int64_t frames, double* d_alpha, Alpha0 a0,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, const AlphaPeers& peers) {
     const int K = (int)m->dim;
     const AffineSmemLayout L = affine_layout(K, KP, MT, STAGES);
     if (L.bytes > 227 * 1024) return 1;  // does not fit: caller tries a smaller configuration
@@ -267,7 +272,7 @@ static int launch_affine_tma_cfg(const rn_model* m, const double* d_in, int64_t 
     if (ctas_per_sm < 1) return 1;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)m->sm_count * ctas_per_sm);
     kern<<<grid, kAffineWarps * 32, L.bytes, stream>>>(d_in, ref, G, frames, K, L.row_stride, L.stage_doubles, a0,
-                                                       d_alpha);
+                                                       d_alpha, peers);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     return RN_OK;
@@ -275,23 +280,23 @@ static int launch_affine_tma_cfg(const rn_model* m, const double* d_in, int64_t 
 
 template <int KP, bool WRAP>
 static int launch_affine_tma_kp(const rn_model* m, const double* d_in, int64_t frames, double* d_alpha, Alpha0 a0,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, const AlphaPeers& peers) {
     // Measured on B200 (tools/tune_affine.py, 1M frames): LLZO (KP=9) 16-frame tiles, 1 CTA/SM:
     // 6284 GB/s; 8-frame tiles, 2 CTAs/SM: 6200 GB/s.  TiO2 (KP=6): 4855 vs 5127 GB/s.
     int mt = g_affine_mt;
     if (mt == 0) mt = (KP >= 8) ? 2 : 1;
     int rc = 1;
-    if (mt == 2) rc = launch_affine_tma_cfg<KP, 2, 2, WRAP>(m, d_in, frames, d_alpha, a0, stream);
-    if (rc == 1) rc = launch_affine_tma_cfg<KP, 1, 2, WRAP>(m, d_in, frames, d_alpha, a0, stream);
+    if (mt == 2) rc = launch_affine_tma_cfg<KP, 2, 2, WRAP>(m, d_in, frames, d_alpha, a0, stream, peers);
+    if (rc == 1) rc = launch_affine_tma_cfg<KP, 1, 2, WRAP>(m, d_in, frames, d_alpha, a0, stream, peers);
     return rc;
 }
 
 template <bool WRAP>
 static int launch_affine_tma(const rn_model* m, const double* d_in, int64_t frames, double* d_alpha, Alpha0 a0,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, const AlphaPeers& peers) {
     switch (m->affine_kp) {
 #define RN_AFFINE_CASE(KP) \
-    case KP: return launch_affine_tma_kp<KP, WRAP>(m, d_in, frames, d_alpha, a0, stream);
+    case KP: return launch_affine_tma_kp<KP, WRAP>(m, d_in, frames, d_alpha, a0, stream, peers);
         RN_AFFINE_CASE(1)
         RN_AFFINE_CASE(2)
         RN_AFFINE_CASE(3)
@@ -328,7 +333,7 @@ static int launch_affine_generic(const rn_model* m, const double* d_in, int64_t 
 static bool g_force_generic_affine = false;
 
 int launch_affine(const rn_model* m, const double* d_in, bool wrap, int64_t num_frames, double* d_alpha,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const AlphaPeers* peers, bool* peers_done) {
     Alpha0 a0;
     for (int q = 0; q < 9; q++) a0.v[q] = m->alpha0[q];
     const int K = (int)m->dim;
@@ -338,15 +343,20 @@ int launch_affine(const rn_model* m, const double* d_in, bool wrap, int64_t num_
         tma_frames = num_frames;
     }
     int rc = RN_OK;
+    AlphaPeers fused;
+    fused.count = 0;
+    if (peers) fused = *peers;
     if (tma_frames > 0) {
-        rc = wrap ? launch_affine_tma<true>(m, d_in, tma_frames, d_alpha, a0, stream)
-                  : launch_affine_tma<false>(m, d_in, tma_frames, d_alpha, a0, stream);
+        rc = wrap ? launch_affine_tma<true>(m, d_in, tma_frames, d_alpha, a0, stream, fused)
+                  : launch_affine_tma<false>(m, d_in, tma_frames, d_alpha, a0, stream, fused);
         if (rc == 1) {  // no configuration fits in shared memory
             tma_frames = 0;
             rc = RN_OK;
         }
         if (rc != RN_OK) return rc;
     }
+    // the TMA kernel stores to the peers itself; the generic fallback does not
+    if (peers_done) *peers_done = (tma_frames == num_frames);
     if (tma_frames < num_frames) {
         rc = wrap ? launch_affine_generic<true>(m, d_in, tma_frames, num_frames, d_alpha, a0, stream)
                   : launch_affine_generic<false>(m, d_in, tma_frames, num_frames, d_alpha, a0, stream);
@@ -592,7 +602,7 @@ int launch_dense_v1(const rn_model* m, const double* d_in, bool wrap, bool accum
 using namespace rn;
 
 static int eval_common(const rn_model* model, const double* d_in, bool wrap, int64_t num_frames, double* d_alpha,
-                       void* stream) {
+                       void* stream, const AlphaPeers* peers = nullptr) {
     RN_CHECK_ARG(model != nullptr, "model is null");
     RN_CHECK_ARG(num_frames >= 0, "num_frames must be non-negative");
     if (num_frames == 0) return RN_OK;
@@ -603,15 +613,44 @@ static int eval_common(const rn_model* model, const double* d_in, bool wrap, int
         return RN_ERR_CUDA;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (model->num_dofs == 0) return launch_fill_alpha0(model, num_frames, d_alpha, s);
+    if (peers && peers->count == 0) peers = nullptr;
     int rc = RN_OK;
-    const bool run_affine = model->num_linear > 0;
-    if (run_affine) {
-        rc = launch_affine(model, d_in, wrap, num_frames, d_alpha, s);
-        if (rc != RN_OK) return rc;
+    bool peers_done = false;
+    if (model->num_dofs == 0) {
+        rc = launch_fill_alpha0(model, num_frames, d_alpha, s);
+    } else {
+        const bool run_affine = model->num_linear > 0;
+        const bool run_dense = model->num_dense > 0;
+        if (run_affine) {
+            // if a dense pass follows, the final rows come from it: fuse the peer stores there
+            rc = launch_affine(model, d_in, wrap, num_frames, d_alpha, s, run_dense ? nullptr : peers, &peers_done);
+            if (rc != RN_OK) return rc;
+        }
+        if (run_dense) rc = launch_dense(model, d_in, wrap, run_affine, num_frames, d_alpha, s, peers, &peers_done);
     }
-    if (model->num_dense > 0) rc = launch_dense(model, d_in, wrap, run_affine, num_frames, d_alpha, s);
-    return rc;
+    if (rc != RN_OK) return rc;
+    if (peers && !peers_done) {  // kernels without fused peer stores: plain device-to-peer copies
+        for (int p = 0; p < peers->count; p++)
+            RN_CUDA(cudaMemcpyAsync(peers->ptr[p], d_alpha, sizeof(double) * 9 * num_frames, cudaMemcpyDeviceToDevice, s));
+    }
+    return RN_OK;
+}
+
+static int make_peers(double* const* d_alpha_outputs, int num_outputs, AlphaPeers* peers) {
+    RN_CHECK_ARG(d_alpha_outputs != nullptr && num_outputs >= 1 && num_outputs <= 8,
+                 "between 1 and 8 output pointers are required");
+    peers->count = num_outputs - 1;
+    for (int i = 0; i < num_outputs; i++) RN_CHECK_ARG(d_alpha_outputs[i] != nullptr, "null output pointer");
+    for (int i = 1; i < num_outputs; i++) peers->ptr[i - 1] = d_alpha_outputs[i];
+    return RN_OK;
+}
+
+extern "C" int rn_calc_polarizabilities_multi(const rn_model* model, const double* d_positions, int64_t num_frames,
+                                              double* const* d_alpha_outputs, int num_outputs, void* stream) {
+    AlphaPeers peers;
+    int rc = make_peers(d_alpha_outputs, num_outputs, &peers);
+    if (rc != RN_OK) return rc;
+    return eval_common(model, d_positions, true, num_frames, d_alpha_outputs[0], stream, &peers);
 }
 
 extern "C" int rn_calc_polarizabilities(const rn_model* model, const double* d_positions, int64_t num_frames,

@@ -166,13 +166,20 @@ extern "C" int rn_host_unregister(void* h_ptr) {
     return RN_OK;
 }
 
-extern "C" int rn_calc_polarizabilities_host(const rn_model* model, const double* h_positions, int64_t num_frames,
-                                             double* h_alpha, double* d_alpha, int64_t chunk_frames) {
+extern "C" int rn_calc_polarizabilities_multi(const rn_model* model, const double* d_positions, int64_t num_frames,
+                                              double* const* d_alpha_outputs, int num_outputs, void* stream);
+
+// Shared implementation of the host-buffer entries: outputs[0] is the local series (or null when
+// only h_alpha is wanted), further outputs are peer GPUs' buffers (fused all-gather).
+static int host_pipeline(const rn_model* model, const double* h_positions, int64_t num_frames, double* h_alpha,
+                         double* const* d_outputs, int num_outputs, int64_t chunk_frames) {
     RN_CHECK_ARG(model != nullptr, "model is null");
     RN_CHECK_ARG(num_frames >= 0, "num_frames must be non-negative");
     if (num_frames == 0) return RN_OK;
     RN_CHECK_ARG(h_positions != nullptr, "null host pointer");
+    double* d_alpha = (num_outputs > 0) ? d_outputs[0] : nullptr;
     RN_CHECK_ARG(h_alpha || d_alpha, "no output buffer given");
+    RN_CHECK_ARG(num_outputs <= 8, "at most 8 output pointers");
     DeviceGuard guard(model->device);
     if (!guard.ok) {
         set_error("cudaSetDevice(%d) failed", model->device);
@@ -194,12 +201,29 @@ extern "C" int rn_calc_polarizabilities_host(const rn_model* model, const double
         cudaStream_t s = pipe.stream[slot];
         // stream order serialises reuse of this slot's buffers; the other slot overlaps
         RN_CUDA(cudaMemcpyAsync(pipe.d_pos[slot], h_positions + f0 * K, sizeof(double) * n * K, cudaMemcpyHostToDevice, s));
-        double* out = d_alpha ? d_alpha + f0 * 9 : pipe.d_alpha[slot];
-        int rc = rn_calc_polarizabilities(model, pipe.d_pos[slot], n, out, s);
+        double* outs[8];
+        int count = 1;
+        outs[0] = d_alpha ? d_alpha + f0 * 9 : pipe.d_alpha[slot];
+        for (int p = 1; p < num_outputs; p++) outs[count++] = d_outputs[p] + f0 * 9;
+        int rc = rn_calc_polarizabilities_multi(model, pipe.d_pos[slot], n, outs, count, s);
         if (rc != RN_OK) return rc;
-        if (h_alpha) RN_CUDA(cudaMemcpyAsync(h_alpha + f0 * 9, out, sizeof(double) * n * 9, cudaMemcpyDeviceToHost, s));
+        if (h_alpha) RN_CUDA(cudaMemcpyAsync(h_alpha + f0 * 9, outs[0], sizeof(double) * n * 9, cudaMemcpyDeviceToHost, s));
     }
     RN_CUDA(cudaStreamSynchronize(pipe.stream[0]));
     RN_CUDA(cudaStreamSynchronize(pipe.stream[1]));
     return RN_OK;
+}
+
+extern "C" int rn_calc_polarizabilities_host(const rn_model* model, const double* h_positions, int64_t num_frames,
+                                             double* h_alpha, double* d_alpha, int64_t chunk_frames) {
+    double* outs[1] = {d_alpha};
+    return host_pipeline(model, h_positions, num_frames, h_alpha, outs, d_alpha ? 1 : 0, chunk_frames);
+}
+
+extern "C" int rn_calc_polarizabilities_host_multi(const rn_model* model, const double* h_positions, int64_t num_frames,
+                                                   double* const* d_alpha_outputs, int num_outputs,
+                                                   int64_t chunk_frames) {
+    RN_CHECK_ARG(d_alpha_outputs != nullptr && num_outputs >= 1, "output pointers are required");
+    for (int i = 0; i < num_outputs; i++) RN_CHECK_ARG(d_alpha_outputs[i] != nullptr, "null output pointer");
+    return host_pipeline(model, h_positions, num_frames, nullptr, d_alpha_outputs, num_outputs, chunk_frames);
 }

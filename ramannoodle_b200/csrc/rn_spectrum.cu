@@ -20,6 +20,7 @@ struct rn_spectrum_plan {
     int sm_count = 0;
     int64_t S = 0, M = 0, L = 0;
     int log2l = 0;
+    int log2tile = 10;
     int num_passes = 0;
     int pass_log2r[4] = {0, 0, 0, 0};
     int split = 0;                // two-level twiddle split: m = hi << split | lo
@@ -112,9 +113,11 @@ __device__ __forceinline__ void dft8(double2* v) {
 enum { LOAD_PLAIN = 0, LOAD_ALPHA = 1, LOAD_SIGNAL = 2 };
 enum { STORE_PLAIN = 0, STORE_POST = 1, STORE_MULH = 2 };
 
-constexpr int kLog2Tile = 10;  // 1024 complex elements per CTA tile
-constexpr int kTileThreads = (1 << kLog2Tile) / 8;
-constexpr int kMaxLog2R = 8;
+constexpr int kMaxLog2R = 8;  // sub-transforms of at most 256 points per pass
+// CTA tile: 1024 complex elements (128 threads, many CTAs per SM) while the transform is L2 resident;
+// 4096 elements (512 threads, 256-byte global chunks) for transforms that stream from HBM.
+constexpr int kLog2TileSmall = 10, kLog2TileLarge = 12;
+constexpr int kLargeTileMinLog2L = 23;
 
 struct PassParams {
     int64_t L;
@@ -155,9 +158,22 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
         if (n < P.M) {
             double d1, d2 = 0.0;
             if (LOAD == LOAD_ALPHA) {
-                // np.diff of the series (_raman.py:282), two tensor components per complex sequence
-                d1 = __ldg(P.src + (n + 1) * 9 + P.c1) - __ldg(P.src + n * 9 + P.c1);
-                d2 = __ldg(P.src + (n + 1) * 9 + P.c2) - __ldg(P.src + n * 9 + P.c2);
+                // np.diff of the series (_raman.py:282), two real signals per complex sequence
+                const double* a = P.src + n * 9;
+                if (P.c1 >= 0) {  // two tensor components
+                    d1 = __ldg(a + 9 + P.c1) - __ldg(a + P.c1);
+                    d2 = __ldg(a + 9 + P.c2) - __ldg(a + P.c2);
+                } else {
+                    const double xx = __ldg(a + 9) - __ldg(a), yy = __ldg(a + 13) - __ldg(a + 4);
+                    const double zz = __ldg(a + 17) - __ldg(a + 8);
+                    if (P.c1 == -1) {  // (xx - yy, yy - zz): the anisotropy differences (_raman.py:289-291)
+                        d1 = xx - yy;
+                        d2 = yy - zz;
+                    } else {  // (trace, xy) (_raman.py:286-288,292)
+                        d1 = xx + yy + zz;
+                        d2 = __ldg(a + 10) - __ldg(a + 1);
+                    }
+                }
             } else {
                 d1 = __ldg(P.src + n);
             }
@@ -277,8 +293,9 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
     }
 }
 
-template <int SGN, int LOAD, int STORE>
-__global__ void __launch_bounds__(kTileThreads, STORE == STORE_MULH ? 4 : 6) fft_tile_kernel(PassParams P) {
+template <int SGN, int LOAD, int STORE, int LOG2TILE>
+__global__ void __launch_bounds__((1 << LOG2TILE) / 8, LOG2TILE == kLog2TileSmall ? (STORE == STORE_MULH ? 4 : 6) : (STORE == STORE_MULH ? 1 : 2))
+    fft_tile_kernel(PassParams P) {
     extern __shared__ __align__(16) unsigned char fft_smem[];
     double2* S = reinterpret_cast<double2*>(fft_smem);
     const int rem = P.log2r % 3;
@@ -296,19 +313,26 @@ struct FftIo {
     double2* spec = nullptr;
 };
 
-template <int SGN, int LOAD, int STORE>
-static int launch_tile_pass(const rn_spectrum_plan* p, const PassParams& P, cudaStream_t stream) {
+template <int SGN, int LOAD, int STORE, int LOG2TILE>
+static int launch_tile_pass_t(const rn_spectrum_plan* p, const PassParams& P, cudaStream_t stream) {
     const int R = 1 << P.log2r, B = 1 << P.log2b;
     const int pitch = (B > 1) ? B + 1 : 1;
     const size_t smem = (size_t)R * pitch * sizeof(double2);
     const int64_t tiles = (P.L >> P.log2r) >> P.log2b;
-    auto kern = fft_tile_kernel<SGN, LOAD, STORE>;
+    auto kern = fft_tile_kernel<SGN, LOAD, STORE, LOG2TILE>;
     (void)p;
-    const int64_t grid = std::min<int64_t>(tiles, (int64_t)1 << 30);  // one tile per CTA; many small CTAs per SM
-    kern<<<(unsigned)grid, kTileThreads, smem, stream>>>(P);
+    if (smem > 48 * 1024) RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = std::min<int64_t>(tiles, (int64_t)1 << 30);  // one tile per CTA
+    kern<<<(unsigned)grid, (1 << LOG2TILE) / 8, smem, stream>>>(P);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     return RN_OK;
+}
+
+template <int SGN, int LOAD, int STORE>
+static int launch_tile_pass(const rn_spectrum_plan* p, const PassParams& P, cudaStream_t stream) {
+    if (p->log2tile == kLog2TileLarge) return launch_tile_pass_t<SGN, LOAD, STORE, kLog2TileLarge>(p, P, stream);
+    return launch_tile_pass_t<SGN, LOAD, STORE, kLog2TileSmall>(p, P, stream);
 }
 
 // Full length-L transform: `first` is read by the first pass (with io.load); passes ping-pong
@@ -325,7 +349,7 @@ static int fft_run(const rn_spectrum_plan* p, const double2* first, double2* las
         PassParams P;
         P.L = p->L;
         P.log2r = p->pass_log2r[i];
-        int log2b = kLog2Tile - P.log2r;
+        int log2b = p->log2tile - P.log2r;
         const int log2cnt = p->log2l - P.log2r;
         if (log2b > log2cnt) log2b = log2cnt;
         if (log2b < 0) log2b = 0;
@@ -527,6 +551,57 @@ __global__ void __launch_bounds__(256) signal_combine_kernel(const double2* __re
     }
 }
 
+// One third of the orientational average, for the sharded (multi-GPU) measure: each part is one
+// packed chirp-z transform, so parts can run on different ranks and their outputs just add up:
+//   part 0: z = (xx-yy) + i (yy-zz)  ->  7 (S_a/2 + S_b/2 + S_c/2),  X_c = -(X_a + X_b)
+//   part 1: z = trace + i xy         ->  45 S_tr/9 + 21 S_xy
+//   part 2: z = yz + i xz            ->  21 (S_yz + S_xz)
+__global__ void __launch_bounds__(256) part_combine_kernel(const double2* __restrict__ spec,
+                                                           const double* __restrict__ energy, int part, int64_t M,
+                                                           int64_t L, int64_t points, double* __restrict__ partial) {
+    const double scale = 1.0 / (double)L;
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < points; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = o + 1;
+        double2 zk = spec[k], zm = spec[M - k];
+        zk.x *= scale; zk.y *= scale; zm.x *= scale; zm.y *= scale;
+        const double2 x1 = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+        const double2 x2 = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+        auto power = [](double2 v, double e) { return (v.x * v.x + v.y * v.y + e) * 0.5; };
+        double out;
+        if (part == 0) {
+            const double2 x3 = make_double2(-(x1.x + x2.x), -(x1.y + x2.y));
+            out = 7.0 * ((1.0 / 2.0) * power(x1, energy[1]) + (1.0 / 2.0) * power(x2, energy[2]) +
+                         (1.0 / 2.0) * power(x3, energy[3]));
+        } else if (part == 1) {
+            out = 45.0 * ((1.0 / 9.0) * power(x1, energy[0])) + 7.0 * (3.0 * power(x2, energy[4]));
+        } else {
+            out = 7.0 * (3.0 * power(x1, energy[5]) + 3.0 * power(x2, energy[6]));
+        }
+        partial[o] = out;
+    }
+}
+
+// wavenumbers + optional corrections on summed partial intensities
+__global__ void __launch_bounds__(256) finish_kernel(const double* __restrict__ partial_sum, int64_t M, int64_t points,
+                                                     SpectrumParams prm, double* __restrict__ wn_out,
+                                                     double* __restrict__ int_out) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < points; o += (int64_t)gridDim.x * blockDim.x) {
+        double inten = partial_sum[o];
+        const double wn = wavenumber_of(o + 1, M, prm.timestep);
+        if (prm.laser) {
+            const double r = (wn - prm.laser_wavenumber) / 10000.0;
+            const double r2 = r * r;
+            inten *= (r2 * r2) / wn;
+        }
+        if (prm.bose_einstein) {
+            const double en = wn * 29979245800.0 * 4.1357e-15;
+            inten *= 1.0 / (1.0 - exp(-en / prm.kt));
+        }
+        wn_out[o] = wn;
+        int_out[o] = inten;
+    }
+}
+
 static int grid_for(int64_t n, int sms) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16));
 }
@@ -609,6 +684,7 @@ extern "C" int rn_spectrum_plan_create(int64_t num_frames, int device, rn_spectr
     p->log2l = log2l;
     // pass structure: sub-transforms of at most 256 points (>= 64-byte global chunks), as even as possible
     p->num_passes = (log2l + kMaxLog2R - 1) / kMaxLog2R;
+    p->log2tile = (log2l >= kLargeTileMinLog2L) ? kLog2TileLarge : kLog2TileSmall;
     for (int i = 0, rem = log2l; i < p->num_passes; i++) {
         const int left = p->num_passes - i;
         p->pass_log2r[i] = (rem + left - 1) / left;
@@ -719,6 +795,60 @@ extern "C" int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, dou
     prm.kt = 8.617333262e-5 * temperature_K;  // constants.py:249
     combine_kernel<<<grid_for(points, plan->sm_count), 256, 0, s>>>(plan->d_spec, plan->d_energy, M, L, points, prm,
                                                                    d_wavenumbers, d_intensities);
+    RN_LAUNCHED();
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}
+
+extern "C" int rn_md_spectrum_part(rn_spectrum_plan* plan, const double* d_alpha, int part, double* d_partial,
+                                   void* stream) {
+    RN_CHECK_ARG(plan != nullptr && d_alpha != nullptr, "null pointer");
+    RN_CHECK_ARG(part >= 0 && part <= 2, "part must be 0, 1 or 2");
+    const int64_t points = rn_spectrum_num_points(plan->S);
+    if (points == 0) return RN_OK;
+    RN_CHECK_ARG(d_partial != nullptr, "null output pointer");
+    DeviceGuard guard(plan->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t M = plan->M, L = plan->L;
+    energy_partial_kernel<0><<<plan->energy_blocks, 256, 0, s>>>(d_alpha, M, plan->d_partial);
+    RN_LAUNCHED();
+    energy_final_kernel<<<1, 256, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
+    RN_LAUNCHED();
+    FftIo io;
+    io.load = LOAD_ALPHA;
+    io.src = d_alpha;
+    if (part == 0) io.c1 = -1;
+    else if (part == 1) io.c1 = -2;
+    else {
+        io.c1 = 5;  // yz
+        io.c2 = 2;  // xz
+    }
+    int rc = bluestein_transform(plan, io, plan->d_spec, s);
+    if (rc != RN_OK) return rc;
+    part_combine_kernel<<<grid_for(points, plan->sm_count), 256, 0, s>>>(plan->d_spec, plan->d_energy, part, M, L, points,
+                                                                        d_partial);
+    RN_LAUNCHED();
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}
+
+extern "C" int rn_md_spectrum_finish(int64_t num_frames, const double* d_partial_sum, double timestep_fs,
+                                     int laser_correction, double laser_wavelength_nm, int bose_einstein_correction,
+                                     double temperature_K, double* d_wavenumbers, double* d_intensities, void* stream) {
+    RN_CHECK_ARG(timestep_fs > 0, "timestep must be positive");
+    if (laser_correction) RN_CHECK_ARG(laser_wavelength_nm > 0, "invalid laser_wavelength");
+    if (bose_einstein_correction) RN_CHECK_ARG(temperature_K > 0, "invalid temperature: %g <= 0", temperature_K);
+    const int64_t points = rn_spectrum_num_points(num_frames);
+    if (points == 0) return RN_OK;
+    RN_CHECK_ARG(d_partial_sum && d_wavenumbers && d_intensities, "null pointer");
+    SpectrumParams prm;
+    prm.timestep = timestep_fs;
+    prm.laser = laser_correction ? 1 : 0;
+    prm.laser_wavenumber = laser_correction ? 10000000.0 / laser_wavelength_nm : 0.0;
+    prm.bose_einstein = bose_einstein_correction ? 1 : 0;
+    prm.kt = 8.617333262e-5 * temperature_K;
+    finish_kernel<<<grid_for(points, 148), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_partial_sum, num_frames - 1, points, prm, d_wavenumbers, d_intensities);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     return RN_OK;

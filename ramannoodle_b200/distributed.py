@@ -9,9 +9,13 @@ halo because it runs after the gather.
 """
 from __future__ import annotations
 
+import ctypes
+
+from . import _lib
 from .abstract import Dynamics
 from .dynamics import Trajectory
-from .spectrum import MDRamanSpectrum
+from .exceptions import get_type_error
+from .spectrum import MDRamanSpectrum, _get_plan, _stream
 
 
 def shard_bounds(num_frames: int, world_size: int, rank: int) -> tuple[int, int]:
@@ -51,6 +55,102 @@ def allgather_series(local_series, num_frames: int, group=None):
     return full[:num_frames]
 
 
+_SYMMETRIC_SERIES: dict = {}
+
+
+def symmetric_series(num_frames: int, device, group=None):
+    """A (S,3,3) fp64 series buffer in symmetric memory (the same allocation on every rank of
+    ``group``, each rank's copy mapped into every other rank's address space over NVLink), plus its
+    rendezvous handle.  Cached per (S, device, group): the rendezvous is a collective."""
+    import torch  # pylint: disable=import-outside-toplevel
+    import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+    import torch.distributed._symmetric_memory as symm_mem  # pylint: disable=import-outside-toplevel
+
+    pg = group if group is not None else dist.group.WORLD
+    key = (int(num_frames), str(device), pg.group_name)
+    entry = _SYMMETRIC_SERIES.get(key)
+    if entry is None:
+        tensor = symm_mem.empty((int(num_frames), 3, 3), dtype=torch.float64, device=device)
+        handle = symm_mem.rendezvous(tensor, group=pg.group_name)
+        entry = (tensor, handle)
+        _SYMMETRIC_SERIES.clear()  # one live buffer: they are as large as the series
+        _SYMMETRIC_SERIES[key] = entry
+    return entry
+
+
+def spectrum_parts(world_size: int, rank: int) -> list[int]:
+    """Which of the three packed transforms of ``measure`` rank ``rank`` computes
+    (``include/ramannoodle_b200.h: rn_md_spectrum_part``): round-robin over the ranks."""
+    return [part for part in range(3) if part % world_size == rank]
+
+
+class ShardedMDRamanSpectrum(MDRamanSpectrum):
+    """``MDRamanSpectrum`` whose ``measure`` is spread over the ranks of a process group.
+
+    Every rank holds the full (S,3,3) series (after the all-gather).  The orientational average
+    45 a^2 + 7 g^2 (``ramannoodle/spectrum/_raman.py:286-297``) is a sum of three independent
+    packed chirp-z transforms; rank r computes parts ``spectrum_parts(G, r)``, the (P,) partial
+    intensities are summed with one all-reduce, and every rank applies the wavenumber grid and
+    the optional corrections.  With G >= 3 the spectrum stage costs one transform instead of three.
+    """
+
+    def __init__(self, polarizability_ts, timestep: float, group=None):
+        super().__init__(polarizability_ts, timestep)
+        self._group = group
+
+    # pylint: disable=too-many-arguments,too-many-positional-arguments,too-many-locals
+    def measure_device(self, orientation="polycrystalline", laser_correction=False, laser_wavelength=522,
+                       bose_einstein_correction=False, temperature=300):
+        import torch  # pylint: disable=import-outside-toplevel
+        import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+
+        if orientation != "polycrystalline":
+            raise NotImplementedError("only polycrystalline spectra are supported for now")
+        if laser_correction:
+            laser_wavenumber = 10000000 / laser_wavelength
+            try:
+                if laser_wavenumber <= 0:
+                    raise ValueError(f"invalid laser_wavenumber: {laser_wavenumber} <= 0")
+            except TypeError as exc:
+                raise get_type_error("laser_wavenumber", laser_wavenumber, "float") from exc
+        if bose_einstein_correction:
+            try:
+                if temperature <= 0:
+                    raise ValueError(f"invalid temperature: {temperature} <= 0")
+            except TypeError as exc:
+                raise get_type_error("temperature", temperature, "float") from exc
+        series = self._device_series()
+        num_frames = int(series.shape[0])
+        if num_frames < 2:
+            raise ValueError("polarizability_ts must contain at least 2 configurations")
+        device = int(series.device.index or 0)
+        world, rank = dist.get_world_size(self._group), dist.get_rank(self._group)
+        points = int(_lib.lib().rn_spectrum_num_points(num_frames))
+        with torch.cuda.device(device):
+            total = torch.zeros(points, dtype=torch.float64, device=series.device)
+            wavenumbers = torch.empty(points, dtype=torch.float64, device=series.device)
+            intensities = torch.empty(points, dtype=torch.float64, device=series.device)
+            if points > 0:
+                parts = spectrum_parts(world, rank)
+                if parts:
+                    plan = _get_plan(num_frames, device)
+                    partial = torch.empty(points, dtype=torch.float64, device=series.device)
+                    for part in parts:
+                        status = _lib.lib().rn_md_spectrum_part(plan.handle, ctypes.c_void_p(series.data_ptr()), part,
+                                                                ctypes.c_void_p(partial.data_ptr()), _stream(device))
+                        _lib.check(status, "rn_md_spectrum_part")
+                        total += partial
+                if world > 1:
+                    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self._group)
+                status = _lib.lib().rn_md_spectrum_finish(
+                    num_frames, ctypes.c_void_p(total.data_ptr()), float(self._timestep),
+                    1 if laser_correction else 0, float(laser_wavelength) if laser_correction else 0.0,
+                    1 if bose_einstein_correction else 0, float(temperature) if bose_einstein_correction else 0.0,
+                    ctypes.c_void_p(wavenumbers.data_ptr()), ctypes.c_void_p(intensities.data_ptr()), _stream(device))
+                _lib.check(status, "rn_md_spectrum_finish")
+        return wavenumbers, intensities
+
+
 class ShardedTrajectory(Dynamics):
     """The local frame block of a trajectory that is sharded over the ranks of a process group.
 
@@ -84,8 +184,22 @@ class ShardedTrajectory(Dynamics):
     def num_frames(self) -> int:
         return self._num_frames
 
-    def get_raman_spectrum(self, polarizability_model) -> MDRamanSpectrum:
-        """Evaluate the local block, all-gather the series, return the full-series spectrum."""
+    def get_raman_spectrum(self, polarizability_model, fused: bool = True,
+                           reuse_series_buffer: bool = False) -> MDRamanSpectrum:
+        """Evaluate the local block and assemble the full (S,3,3) series on every rank; returns a
+        ``ShardedMDRamanSpectrum`` (its ``measure`` is spread over the ranks too).
+
+        ``fused=True`` (default, CUDA + NCCL groups with this package's models): the series lives
+        in symmetric memory and the evaluation kernels store every row to all ranks' copies over
+        NVLink themselves, so the all-gather overlaps the evaluation; two device-side barriers
+        bracket the stores.  Otherwise (or if symmetric memory is unavailable) the local block is
+        evaluated first and one ``all_gather_into_tensor`` assembles the series.
+        ``reuse_series_buffer=True`` hands out the symmetric buffer itself (overwritten by the next
+        call) instead of a copy."""
+        if fused:
+            spectrum = self._get_raman_spectrum_fused(polarizability_model, reuse_series_buffer)
+            if spectrum is not None:
+                return spectrum
         local = self._local.get_raman_spectrum(polarizability_model)
         series = local._polarizability_ts  # pylint: disable=protected-access
         if not hasattr(series, "data_ptr"):
@@ -93,4 +207,32 @@ class ShardedTrajectory(Dynamics):
 
             series = torch.from_numpy(series)
         full = allgather_series(series, self._num_frames, self._group)
-        return MDRamanSpectrum(full, self._local.timestep)
+        return ShardedMDRamanSpectrum(full, self._local.timestep, self._group)
+
+    def _get_raman_spectrum_fused(self, polarizability_model, reuse_series_buffer: bool):
+        import torch  # pylint: disable=import-outside-toplevel
+        import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+
+        multi = getattr(polarizability_model, "calc_polarizabilities_multi", None)
+        if multi is None or not torch.cuda.is_available() or dist.get_backend(self._group) != "nccl":
+            return None
+        world, rank = dist.get_world_size(self._group), dist.get_rank(self._group)
+        if world == 1 or world > 8:
+            return None
+        positions = self._local._positions_ts  # pylint: disable=protected-access
+        device = positions.device if hasattr(positions, "data_ptr") else torch.device("cuda", torch.cuda.current_device())
+        try:
+            series, handle = symmetric_series(self._num_frames, device, self._group)
+        except Exception:  # pylint: disable=broad-except  (no symmetric-memory support on this system)
+            return None
+        start, _ = shard_bounds(self._num_frames, world, rank)
+        order = [rank] + [r for r in range(world) if r != rank]  # local copy first
+        ptrs = [int(handle.buffer_ptrs[r]) + start * 72 for r in order]
+        handle.barrier()  # every rank is done with the previous contents of the buffers
+        try:
+            multi(positions, ptrs)
+        except ValueError as exc:
+            raise ValueError("polarizability_model and trajectory are incompatible") from exc
+        handle.barrier()  # every rank's rows have landed everywhere
+        full = series if reuse_series_buffer else series.clone()
+        return ShardedMDRamanSpectrum(full, self._local.timestep, self._group)

@@ -216,6 +216,44 @@ class InterpolationModel(PolarizabilityModel):
         _lib.check(status, "rn_calc_polarizabilities_host")
         return alpha
 
+    def calc_polarizabilities_multi(self, positions_batch, output_ptrs) -> None:
+        """Evaluate ``positions_batch`` (numpy, streamed from the host, or a CUDA tensor) and store
+        the (S,3,3) rows to every device pointer in ``output_ptrs`` (ints): ``output_ptrs[0]`` is
+        the local series, the others the same buffer on peer GPUs (symmetric memory over NVLink),
+        all pre-offset to this rank's first frame.  The kernels write the peers' rows themselves —
+        the all-gather is fused into the evaluation (``rn_calc_polarizabilities_multi``)."""
+        count = len(output_ptrs)
+        if not 1 <= count <= 8:
+            raise ValueError("between 1 and 8 output pointers are required")
+        outputs = (ctypes.c_void_p * count)(*[ctypes.c_void_p(int(ptr)) for ptr in output_ptrs])
+        if _is_torch_tensor(positions_batch):
+            import torch  # pylint: disable=import-outside-toplevel
+
+            if not positions_batch.is_cuda:
+                raise get_type_error("positions", positions_batch, "ndarray or CUDA tensor")
+            if positions_batch.ndim != 3 or tuple(positions_batch.shape[1:]) != (self.num_atoms, 3):
+                raise get_shape_error("positions", positions_batch, f"(_,{self.num_atoms},3)")
+            self._check_dummy()
+            data = positions_batch.to(torch.float64).contiguous()
+            device = self._resolve_device(data)
+            native = self._native_model(device)
+            with torch.cuda.device(device):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+                status = _lib.lib().rn_calc_polarizabilities_multi(
+                    native.handle, ctypes.c_void_p(data.data_ptr()), int(data.shape[0]), outputs, count, stream)
+            _lib.check(status, "rn_calc_polarizabilities_multi")
+            return
+        if not isinstance(positions_batch, np.ndarray):
+            raise get_type_error("positions", positions_batch, "ndarray")
+        if positions_batch.ndim != 3 or positions_batch.shape[1:] != (self.num_atoms, 3):
+            raise get_shape_error("positions", positions_batch, f"(_,{self.num_atoms},3)")
+        self._check_dummy()
+        positions = np.ascontiguousarray(positions_batch, dtype=np.float64)
+        native = self._native_model()
+        status = _lib.lib().rn_calc_polarizabilities_host_multi(native.handle, _ptr(positions), positions.shape[0],
+                                                                outputs, count, 0)
+        _lib.check(status, "rn_calc_polarizabilities_host_multi")
+
     def get_polarizability(self, cart_displacements):
         """Polarizabilities from precomputed Cartesian displacements (S,N,3) or (S,3N) in Å
         (what ``_interpolation.py:217-223`` produces)."""

@@ -148,7 +148,7 @@ def test_spectrum_error_behaviour():
         rb.convolve_spectrum(np.array([1.0, 2.0, 3.0]), np.array([0.0, 3.0]), "gaussian", 5)
 
 
-@pytest.mark.parametrize("log2l", [3, 4, 5, 6, 7, 9, 10, 12, 13, 14, 16, 17, 20, 21, 22])
+@pytest.mark.parametrize("log2l", [3, 4, 5, 6, 7, 9, 10, 12, 13, 14, 16, 17, 20, 21, 22, 23, 24])
 def test_tiled_fft_against_torch(log2l):
     """The hand-written tiled Stockham FFT (1, 2 and 3 global passes; first sub-pass radix 2, 4
     and 8) against torch.fft (cuFFT) in both directions."""
@@ -174,3 +174,40 @@ def test_tiled_fft_against_torch(log2l):
         got = torch.view_as_complex(out)
         err = float((got - ref).abs().max() / ref.abs().max())
         assert err < 1e-13, f"L=2^{log2l} sign={sign}: {err}"
+
+
+@pytest.mark.parametrize("frames", [41, 1000, 4097, 50_001])
+def test_sharded_parts_sum_to_measure(frames):
+    """The three packed transforms of the sharded measure (rn_md_spectrum_part) add up to
+    MDRamanSpectrum.measure (oracle parity for the multi-GPU spectrum path on one GPU)."""
+    import ctypes
+
+    from ramannoodle_b200 import _lib
+    from ramannoodle_b200.distributed import spectrum_parts
+    from ramannoodle_b200.spectrum import _get_plan
+
+    rng = np.random.default_rng(frames)
+    steps = np.arange(frames)[:, None, None]
+    alpha = (6.0 * np.eye(3)[None] + 0.05 * np.sin(0.011 * steps + rng.uniform(0, 6, (1, 3, 3)))
+             + 0.01 * rng.normal(size=(frames, 3, 3)))
+    ref_wn, ref_inten = ora.md_measure(alpha, 2.0, laser_correction=True, laser_wavelength=532,
+                                       bose_einstein_correction=True, temperature=250)
+    d_alpha = to_cuda(alpha)
+    lib = _lib.lib()
+    plan = _get_plan(frames, 0)
+    points = int(lib.rn_spectrum_num_points(frames))
+    total = torch.zeros(points, dtype=torch.float64, device="cuda:0")
+    part = torch.empty_like(total)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert sorted(spectrum_parts(2, 0) + spectrum_parts(2, 1)) == [0, 1, 2]
+    assert [spectrum_parts(8, r) for r in range(4)] == [[0], [1], [2], []]
+    for index in range(3):
+        assert lib.rn_md_spectrum_part(plan.handle, ctypes.c_void_p(d_alpha.data_ptr()), index,
+                                       ctypes.c_void_p(part.data_ptr()), stream) == 0
+        total += part
+    wn = torch.empty_like(total)
+    inten = torch.empty_like(total)
+    assert lib.rn_md_spectrum_finish(frames, ctypes.c_void_p(total.data_ptr()), 2.0, 1, 532.0, 1, 250.0,
+                                     ctypes.c_void_p(wn.data_ptr()), ctypes.c_void_p(inten.data_ptr()), stream) == 0
+    assert np.array_equal(wn.cpu().numpy(), ref_wn)
+    assert pointwise_rel_err(inten.cpu().numpy(), ref_inten) <= INTENSITY_RTOL

@@ -23,11 +23,11 @@ for structure, kind, frames in (("LLZO", "art", 5001), ("STO", "cubic", 1237)):
     positions = synthetic.make_trajectory(structure, frames, seed=99)
     start, stop = shard_bounds(frames, world, rank)
     model = (rb.ARTModel if kind == "art" else rb.InterpolationModel)(state, device=local)
-    for resident in (False, True):
+    for resident, fused in ((False, True), (True, True), (True, False), (False, False)):
         block = positions[start:stop]
         if resident:
             block = torch.from_numpy(block).to(f"cuda:{local}")
-        spectrum = ShardedTrajectory(block, 1.0, frames).get_raman_spectrum(model)
+        spectrum = ShardedTrajectory(block, 1.0, frames).get_raman_spectrum(model, fused=fused)
         wn, inten = spectrum.measure(laser_correction=True, bose_einstein_correction=True)
         omodel = ora.OracleModel(state.ref_positions, state.lattice, state.ref_polarizability,
                                  list(state.basis_vectors), list(state.splines), state.mask)
@@ -38,7 +38,9 @@ for structure, kind, frames in (("LLZO", "art", 5001), ("STO", "cubic", 1237)):
         e_i = np.max(np.abs(inten - want_int) / np.abs(want_int))
         good = alpha.shape == (frames, 3, 3) and e_a <= 1e-10 and e_i <= 1e-8 and np.array_equal(wn, want_wn)
         ok = ok and good
-        print(f"rank {rank}/{world} {structure}/{kind} resident={resident}: alpha {e_a:.1e} intensity {e_i:.1e} ok={good}",
+        from ramannoodle_b200 import distributed as rdist
+        used_symm = bool(rdist._SYMMETRIC_SERIES)
+        print(f"rank {rank}/{world} {structure}/{kind} resident={resident} fused={fused} symm={used_symm}: alpha {e_a:.1e} intensity {e_i:.1e} ok={good}",
               flush=True)
 flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -106,7 +106,7 @@ static AffineSmemLayout affine_layout(int K, int kp, int mt, int stages) {
     const int slack = kAffineWarps * 8 * kp;  // fragment loads may run past the last row (values are masked)
     L.stage_doubles = 8 * mt * L.row_stride;
     L.bytes = (size_t)(stages * L.stage_doubles + slack) * 8 + (size_t)2 * kAffineWarps * 8 * mt * kRedStride * 8 +
-              (size_t)2 * slack * 8 + (size_t)stages * 8 + 64;
+              (size_t)2 * slack * 8 + (size_t)2 * 8 * mt * 9 * 8 + (size_t)stages * 8 + 64;
     return L;
 }
 
@@ -120,7 +120,7 @@ template <int KP, int MT, int STAGES, bool WRAP>
 __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 1)
     affine_tma_kernel(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ G,
                       int64_t num_frames, int K, int row_stride, int stage_doubles, Alpha0 a0,
-                      double* __restrict__ alpha, AlphaPeers peers) {
+                      double* __restrict__ alpha, AlphaPeers peers, int peers_bulk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ROWS = 8 * MT;
     constexpr int RED = kAffineWarps * ROWS * kRedStride;  // doubles per reduction buffer
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
     double* red = stages + STAGES * stage_doubles + slack;
     double* tab_ref = red + 2 * RED;       // [kAffineWarps*8*KP] wrapped reference positions
     double* tab_g9 = tab_ref + slack;      // [kAffineWarps*8*KP] column 8 of G
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tab_g9 + slack);
+    double* outbuf = tab_g9 + slack;       // [2][ROWS*9] finished rows staged for the bulk stores to the peers
+    uint64_t* bars = reinterpret_cast<uint64_t*>(outbuf + 2 * ROWS * 9);
     const uint32_t full0 = smem_u32(bars);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,8 +181,11 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
     double* myred = red + ((size_t)warp * ROWS + g) * kRedStride;
 
     int64_t i = 0;
+    int64_t pending_tile = -1;  // tile whose rows sit in outbuf waiting for their bulk stores
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
         const int s = (int)(i % STAGES);
+        // full tiles go to the peers as bulk stores; a partial last tile uses plain stores
+        const bool stage_rows = peers_bulk && (tile * ROWS + ROWS <= num_frames);
         mbar_wait(full0 + 8 * s, (uint32_t)(i / STAGES) & 1);
         const double* base = stages + (size_t)s * stage_doubles + rowoff;
         // independent accumulator chains (2 per 8-frame group): one DMMA/DFMA dependency chain
@@ -223,6 +227,17 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
             if (t == 0) slot[(size_t)m * 8 * kRedStride + 8] = a9s;
         }
         __syncthreads();  // partials visible; every warp is done reading stage s
+        if (peers_bulk && threadIdx.x == 32 && pending_tile >= 0) {
+            // fused all-gather: the previous tile's finished rows (staged in smem, complete since this
+            // barrier) go to every peer GPU as one TMA bulk store each (UBLKCP S2G over NVLink)
+            const uint32_t src = smem_u32(outbuf + (size_t)((i - 1) & 1) * ROWS * 9);
+            for (int p = 0; p < peers.count; p++)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                                 peers.ptr[p] + pending_tile * (int64_t)(ROWS * 9)),
+                             "r"(src), "r"((uint32_t)(ROWS * 72))
+                             : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         {
             // refill stage s: thread 0 arms the barrier, lane 0 of warp w copies rows w, w+8, ...
             const int64_t next = tile + (int64_t)STAGES * gridDim.x;
@@ -244,13 +259,34 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
 #pragma unroll
             for (int w = 0; w < kAffineWarps; w++) sum += r[(size_t)w * ROWS * kRedStride];
             const int64_t frame = tile * ROWS + f;
-            if (frame < num_frames) {
-                const double value = sum + a0.v[q];
-                alpha[frame * 9 + q] = value;
-                // fused all-gather: the same row goes to every peer GPU's series over NVLink
+            const double value = sum + a0.v[q];
+            if (frame < num_frames) alpha[frame * 9 + q] = value;
+            if (stage_rows) {
+                outbuf[(size_t)(i & 1) * ROWS * 9 + threadIdx.x] = value;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async-proxy reads
+            } else if (frame < num_frames) {
+                // partial last tile / unaligned peers: plain stores over NVLink
                 for (int p = 0; p < peers.count; p++) peers.ptr[p][frame * 9 + q] = value;
             }
         }
+        if (peers_bulk && threadIdx.x == 32) {
+            // the staging buffer written two tiles from now must not be read by a bulk store any more
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        pending_tile = stage_rows ? tile : -1;
+    }
+    if (peers_bulk) {
+        __syncthreads();
+        if (threadIdx.x == 32 && pending_tile >= 0) {
+            const uint32_t src = smem_u32(outbuf + (size_t)((i - 1) & 1) * ROWS * 9);
+            for (int p = 0; p < peers.count; p++)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                                 peers.ptr[p] + pending_tile * (int64_t)(ROWS * 9)),
+                             "r"(src), "r"((uint32_t)(ROWS * 72))
+                             : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (threadIdx.x == 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
@@ -271,8 +307,12 @@ static int launch_affine_tma_cfg(const rn_model* m, const double* d_in, int64_t 
     RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kAffineWarps * 32, L.bytes));
     if (ctas_per_sm < 1) return 1;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)m->sm_count * ctas_per_sm);
+    // bulk (TMA) stores to the peers need 16-byte aligned destinations
+    int peers_bulk = peers.count > 0 ? 1 : 0;
+    for (int p = 0; p < peers.count; p++)
+        if (reinterpret_cast<uintptr_t>(peers.ptr[p]) % 16 != 0) peers_bulk = 0;
     kern<<<grid, kAffineWarps * 32, L.bytes, stream>>>(d_in, ref, G, frames, K, L.row_stride, L.stage_doubles, a0,
-                                                       d_alpha, peers);
+                                                       d_alpha, peers, peers_bulk);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     return RN_OK;

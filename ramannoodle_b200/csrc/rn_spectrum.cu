@@ -116,7 +116,7 @@ enum { STORE_PLAIN = 0, STORE_POST = 1, STORE_MULH = 2 };
 constexpr int kMaxLog2R = 8;  // sub-transforms of at most 256 points per pass
 // CTA tile: 1024 complex elements (128 threads, many CTAs per SM) while the transform is L2 resident;
 // 4096 elements (512 threads, 256-byte global chunks) for transforms that stream from HBM.
-constexpr int kLog2TileSmall = 10, kLog2TileLarge = 12;
+constexpr int kLog2TileSmall = 10, kLog2TileLarge = 11;
 constexpr int kLargeTileMinLog2L = 23;
 
 struct PassParams {
@@ -214,20 +214,29 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
 
         // ---- first sub-pass (pass twiddle, radix RAD, no sub-twiddle) ----
         if (active) {
+            auto tw = [&](int64_t m) {  // W_L^m (SGN-conjugated) from the two-level table
+                const double2 a = __ldg(P.whi + (m >> P.split));
+                const double2 bb = __ldg(P.wlo + (m & (((int64_t)1 << P.split) - 1)));
+                double2 w = cmul(a, bb);
+                if (SGN > 0) w.y = -w.y;
+                return w;
+            };
+            const int b0 = tid & (B - 1);  // u = tid + t*T keeps the same batch member (T is a multiple of B)
+            const int64_t k = (j_base + b0) & (P.Ns - 1);
+            // element x = i + q*nbf carries W^{k x stride} = W^{k i stride} (W^{k nbf stride})^q:
+            // one table lookup per butterfly plus one shared step instead of one lookup per element
+            double2 wstep = make_double2(1.0, 0.0);
+            if (P.Ns > 1) wstep = tw(k * nbf * P.tw_stride);
 #pragma unroll
             for (int t = 0; t < PER; t++) {
                 const int u = tid + t * T;
                 const int i = u >> P.log2b, b = u & (B - 1);
                 if (P.Ns > 1) {
-                    const int64_t k = (j_base + b) & (P.Ns - 1);
+                    double2 w = tw(k * i * P.tw_stride);
 #pragma unroll
                     for (int q = 0; q < RAD; q++) {
-                        const int64_t m = k * (i + q * nbf) * P.tw_stride;
-                        const double2 a = __ldg(P.whi + (m >> P.split));
-                        const double2 bb = __ldg(P.wlo + (m & (((int64_t)1 << P.split) - 1)));
-                        double2 w = cmul(a, bb);
-                        if (SGN > 0) w.y = -w.y;
                         v[t * RAD + q] = cmul(v[t * RAD + q], w);
+                        if (q + 1 < RAD) w = cmul(w, wstep);
                     }
                 }
                 if (RAD == 8) dft8<SGN>(v + RAD * t);
@@ -294,7 +303,7 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
 }
 
 template <int SGN, int LOAD, int STORE, int LOG2TILE>
-__global__ void __launch_bounds__((1 << LOG2TILE) / 8, LOG2TILE == kLog2TileSmall ? (STORE == STORE_MULH ? 4 : 6) : (STORE == STORE_MULH ? 1 : 2))
+__global__ void __launch_bounds__((1 << LOG2TILE) / 8, LOG2TILE == kLog2TileSmall ? (STORE == STORE_MULH ? 4 : 6) : (STORE == STORE_MULH ? 2 : 3))
     fft_tile_kernel(PassParams P) {
     extern __shared__ __align__(16) unsigned char fft_smem[];
     double2* S = reinterpret_cast<double2*>(fft_smem);

@@ -103,13 +103,16 @@ struct HostPipe {
     double* d_pos[2] = {nullptr, nullptr};
     double* d_alpha[2] = {nullptr, nullptr};
     cudaStream_t stream[2] = {nullptr, nullptr};
-    ~HostPipe() {
+    void release() {
         for (int i = 0; i < 2; i++) {
             if (d_pos[i]) cudaFree(d_pos[i]);
             if (d_alpha[i]) cudaFree(d_alpha[i]);
             if (stream[i]) cudaStreamDestroy(stream[i]);
+            d_pos[i] = d_alpha[i] = nullptr;
+            stream[i] = nullptr;
         }
     }
+    // no destructor: at process exit the CUDA context may already be gone
 };
 
 }  // namespace rn
@@ -186,14 +189,36 @@ static int host_pipeline(const rn_model* model, const double* h_positions, int64
         return RN_ERR_CUDA;
     }
     const int64_t K = model->dim;
-    if (chunk_frames <= 0) chunk_frames = std::max<int64_t>(8, (int64_t)(64ll << 20) / (K * 8));  // ~64 MiB chunks
+    // ~256 MiB chunks: measured on B200 (tools/e2e_probe2.py) 64 MiB chunks show sporadic multi-100-ms
+    // stalls, 256 MiB chunks run at a steady ~48 GB/s of the 55 GB/s pinned-copy rate
+    if (chunk_frames <= 0) chunk_frames = std::max<int64_t>(8, (int64_t)(256ll << 20) / (K * 8));
     chunk_frames = std::min(chunk_frames, num_frames);
     chunk_frames = (chunk_frames + 7) / 8 * 8;
-    HostPipe pipe;
-    for (int i = 0; i < 2; i++) {
-        RN_CUDA(cudaStreamCreateWithFlags(&pipe.stream[i], cudaStreamNonBlocking));
-        RN_CUDA(cudaMalloc((void**)&pipe.d_pos[i], sizeof(double) * chunk_frames * K));
-        if (!d_alpha) RN_CUDA(cudaMalloc((void**)&pipe.d_alpha[i], sizeof(double) * chunk_frames * 9));
+    // staging buffers and streams are cached per thread (allocation / free would serialise the device)
+    static thread_local HostPipe pipe;
+    static thread_local int pipe_device = -1;
+    static thread_local int64_t pipe_pos_doubles = 0, pipe_alpha_doubles = 0;
+    if (pipe_device != model->device) {
+        pipe.release();
+        pipe_device = model->device;
+        pipe_pos_doubles = pipe_alpha_doubles = 0;
+        for (int i = 0; i < 2; i++) RN_CUDA(cudaStreamCreateWithFlags(&pipe.stream[i], cudaStreamNonBlocking));
+    }
+    if (pipe_pos_doubles < chunk_frames * K) {
+        for (int i = 0; i < 2; i++) {
+            if (pipe.d_pos[i]) RN_CUDA(cudaFree(pipe.d_pos[i]));
+            pipe.d_pos[i] = nullptr;
+            RN_CUDA(cudaMalloc((void**)&pipe.d_pos[i], sizeof(double) * chunk_frames * K));
+        }
+        pipe_pos_doubles = chunk_frames * K;
+    }
+    if (!d_alpha && pipe_alpha_doubles < chunk_frames * 9) {
+        for (int i = 0; i < 2; i++) {
+            if (pipe.d_alpha[i]) RN_CUDA(cudaFree(pipe.d_alpha[i]));
+            pipe.d_alpha[i] = nullptr;
+            RN_CUDA(cudaMalloc((void**)&pipe.d_alpha[i], sizeof(double) * chunk_frames * 9));
+        }
+        pipe_alpha_doubles = chunk_frames * 9;
     }
     int slot = 0;
     for (int64_t f0 = 0; f0 < num_frames; f0 += chunk_frames, slot ^= 1) {

@@ -32,6 +32,8 @@ WORKLOADS = {
     "c1": ("TiO2", "art", 10_000, "ARTModel rutile TiO2 (108 atoms, 324 DOFs), 10k-frame synthetic trajectory"),
     "c2": ("STO", "cubic", 100_000, "InterpolationModel cubic BSpline, SrTiO3 (135 atoms, 405 DOFs), 100k frames"),
     "c3": ("LLZO", "art", 1_000_000, "ARTModel LLZO (192 atoms, 576 DOFs), 1M-frame synthetic trajectory per GPU"),
+    "c5": ("LLZO_2x2x2", "cubic4600", 37_888,
+           "InterpolationModel (cubic BSpline) of the 1536-atom LLZO 2x2x2 supercell, 4600 DOFs, 37,888 frames per GPU"),
     "c3dense": ("LLZO", "art", 200_000, "LLZO ARTModel forced through the dense DMMA projection, 200k frames per GPU"),
 }
 
@@ -136,7 +138,8 @@ def _cpu_chunk(args):
     from oracle import numpy_port as ora
     from ramannoodle_b200 import synthetic
 
-    state = synthetic.make_model(structure, kind)
+    state = (synthetic.make_model(structure, "cubic", num_dofs=4600) if kind == "cubic4600"
+             else synthetic.make_model(structure, kind))
     omodel = ora.OracleModel(ref_positions=state.ref_positions, lattice=state.lattice,
                              ref_polarizability=state.ref_polarizability, basis_vectors=list(state.basis_vectors),
                              splines=list(state.splines), mask=state.mask)
@@ -231,7 +234,10 @@ def run_b200(args):
     if args.frames > 0:
         frames = args.frames
     force_dense = args.workload == "c3dense"
-    state = synthetic.make_model(structure, kind)
+    if kind == "cubic4600":
+        state = synthetic.make_model(structure, "cubic", num_dofs=4600)
+    else:
+        state = synthetic.make_model(structure, kind)
     model = (rb.ARTModel if kind == "art" else rb.InterpolationModel)(state, device=local_rank, force_dense=force_dense)
     num_atoms = state.num_atoms
     total_frames = frames * world

@@ -11,6 +11,7 @@
 // three complex sequences; the invariant combinations (trace, xx-yy, ...) are formed in the
 // frequency domain (FFT linearity), their energies in the time domain.
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 
 #include "rn_common.cuh"
@@ -117,7 +118,7 @@ constexpr int kMaxLog2R = 8;  // sub-transforms of at most 256 points per pass
 // CTA tile: 1024 complex elements (128 threads, many CTAs per SM) while the transform is L2 resident;
 // 4096 elements (512 threads, 256-byte global chunks) for transforms that stream from HBM.
 constexpr int kLog2TileSmall = 10, kLog2TileLarge = 11;
-constexpr int kLargeTileMinLog2L = 23;
+constexpr int kLargeTileMinLog2L = 22;
 
 struct PassParams {
     int64_t L;
@@ -693,7 +694,9 @@ extern "C" int rn_spectrum_plan_create(int64_t num_frames, int device, rn_spectr
     p->log2l = log2l;
     // pass structure: sub-transforms of at most 256 points (>= 64-byte global chunks), as even as possible
     p->num_passes = (log2l + kMaxLog2R - 1) / kMaxLog2R;
-    p->log2tile = (log2l >= kLargeTileMinLog2L) ? kLog2TileLarge : kLog2TileSmall;
+    int large_min = kLargeTileMinLog2L;
+    if (const char* env = getenv("RN_FFT_LARGE_TILE_MIN_LOG2L")) large_min = atoi(env);  // tuning hook
+    p->log2tile = (log2l >= large_min) ? kLog2TileLarge : kLog2TileSmall;
     for (int i = 0, rem = log2l; i < p->num_passes; i++) {
         const int left = p->num_passes - i;
         p->pass_log2r[i] = (rem + left - 1) / left;

@@ -212,3 +212,17 @@ def test_large_batch_linearity_property():
     want = ora.calc_polarizabilities(oracle_model(state), pos[sel].cpu().numpy())
     got = model.calc_polarizabilities(pos)[sel].cpu().numpy()
     assert rel_err(got, want) <= ALPHA_RTOL
+
+
+def test_c5_llzo_supercell_1536_atoms():
+    """BASELINE.json configs[4] shape: 1536-atom LLZO 2x2x2 supercell, InterpolationModel with
+    ~4600 DOFs of mixed degree 1-3 (170 MB basis, streamed from HBM/L2), on a few hundred frames."""
+    state = synthetic.make_model("LLZO_2x2x2", "mixed", num_dofs=4600, masked_fraction=0.05, seed=5)
+    positions = synthetic.make_trajectory("LLZO_2x2x2", 300, seed=12)
+    model = rb.InterpolationModel(state)
+    got = model.calc_polarizabilities(to_cuda(positions)).cpu().numpy()
+    sel = np.r_[0:24, 150:158, 292:300]
+    want = ora.calc_polarizabilities(oracle_model(state), positions[sel])
+    assert rel_err(got[sel], want) <= ALPHA_RTOL
+    info = model.path_info()
+    assert info["num_atoms"] == 1536 and info["affine_dofs"] + info["dense_dofs"] == 4600

@@ -8,6 +8,7 @@ Writes
   tests/golden/synthetic_cases.npz       reference outputs for seeded synthetic models/trajectories
   tests/golden/spectrum_cases.npz        reference measure()/calc_signal_spectrum outputs
   tests/golden/smearing.npz              the reference's own known_{gaussian,lorentzian}_spectrum goldens
+  tests/golden/phonons_tio2.npz          Phonons.get_raman_spectrum / PhononRamanSpectrum.measure (next row N1)
 Everything here is produced by importing the reference through ``oracle/ref_bootstrap.py``
 (spglib/defusedxml stubbed; hot-path arithmetic untouched).  The GPU box has no reference
 tree: tests there read only these files.
@@ -186,6 +187,36 @@ def make_spectrum() -> None:
     np.savez_compressed(os.path.join(GOLDEN, "spectrum_cases.npz"), **out)
 
 
+def make_phonons() -> None:
+    """Phonon path through the same evaluator: TiO2 phonons (every 4th mode of
+    ``test/data/TiO2/phonons_OUTCAR``) x the P1 cubic model of ``make_real_tio2``."""
+    import warnings
+
+    import ramannoodle.io.generic as generic_io
+    from ramannoodle.dynamics._phonon import Phonons
+    from ramannoodle.pmodel._interpolation import InterpolationModel
+
+    data_dir = os.path.join(REFERENCE_ROOT, "test/data/TiO2")
+    structure = generic_io.read_ref_structure(f"{data_dir}/phonons_OUTCAR", file_format="outcar")
+    _, ref_pol = generic_io.read_positions_and_polarizability(f"{data_dir}/ref_eps_OUTCAR", file_format="outcar")
+    phonons = generic_io.read_phonons(f"{data_dir}/phonons_OUTCAR", file_format="outcar")
+    keep = slice(0, None, 4)
+    sub = Phonons(phonons.ref_positions, phonons.wavenumbers[keep], phonons.displacements[keep])
+    model = InterpolationModel(structure, ref_pol)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for atom in ("Ti5", "O43"):
+            for direction in "xyz":
+                files = [f"{data_dir}/{atom}_{s}{direction}_eps_OUTCAR" for s in ("0.1", "0.2", "m0.1", "m0.2")]
+                model.add_dof_from_files(files, file_format="outcar", interpolation_order=3)
+    spectrum = sub.get_raman_spectrum(model)
+    wn, inten = spectrum.measure(laser_correction=True, laser_wavelength=532, bose_einstein_correction=True,
+                                 temperature=300)
+    out = {"ref_positions": sub.ref_positions, "wavenumbers": sub.wavenumbers, "displacements": sub.displacements,
+           "raman_tensors": spectrum.raman_tensors, "measure_wavenumbers": wn, "measure_intensities": inten}
+    np.savez_compressed(os.path.join(GOLDEN, "phonons_tio2.npz"), **out)
+
+
 def make_smearing() -> None:
     """The reference's own goldens for ``convolve_spectrum``
     (``test/tests/test_phonon_spectrum.py:403-449``)."""
@@ -206,6 +237,7 @@ def main() -> None:
     make_real_tio2()
     make_synthetic()
     make_spectrum()
+    make_phonons()
     for path in sorted(glob.glob(os.path.join(GOLDEN, "*.npz")) + glob.glob(os.path.join(DATA, "*.npz"))):
         print(f"{os.path.getsize(path):>9d}  {os.path.relpath(path, REPO)}")
 

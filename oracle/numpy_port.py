@@ -240,3 +240,40 @@ def get_raman_spectrum(model: OracleModel, positions_ts, timestep, **measure_kwa
     """Trajectory.get_raman_spectrum + measure — dynamics/_trajectory.py:71-90."""
     alpha = calc_polarizabilities(model, trajectory_positions(positions_ts))
     return md_measure(alpha, timestep, **measure_kwargs)
+
+
+# --------------------------------------------------------------------------------------
+# dynamics/_phonon.py + PhononRamanSpectrum (SURVEY.md §8f row N1)
+# --------------------------------------------------------------------------------------
+RAMAN_TENSOR_CENTRAL_DIFFERENCE = 0.001  # ramannoodle/constants.py:248
+
+
+def phonon_raman_tensors(model: OracleModel, ref_positions, displacements):
+    """``Phonons.get_raman_spectrum`` — ramannoodle/dynamics/_phonon.py:82-108: central
+    differences, two S=1 ``calc_polarizabilities`` calls per mode."""
+    raman_tensors = []
+    for displacement in displacements:
+        epsilon = displacement * RAMAN_TENSOR_CENTRAL_DIFFERENCE
+        plus = calc_polarizabilities(model, np.array([ref_positions + epsilon]))[0]
+        minus = calc_polarizabilities(model, np.array([ref_positions - epsilon]))[0]
+        raman_tensors.append((plus - minus) / RAMAN_TENSOR_CENTRAL_DIFFERENCE)
+    return np.array(raman_tensors)
+
+
+def phonon_measure(phonon_wavenumbers, raman_tensors, laser_correction=False, laser_wavelength=522,
+                   bose_einstein_correction=False, temperature=300):
+    """``PhononRamanSpectrum.measure`` — ramannoodle/spectrum/_raman.py:128-194."""
+    alpha_squared = ((raman_tensors[:, 0, 0] + raman_tensors[:, 1, 1] + raman_tensors[:, 2, 2]) / 3.0) ** 2
+    gamma_squared = (
+        (raman_tensors[:, 0, 0] - raman_tensors[:, 1, 1]) ** 2
+        + (raman_tensors[:, 0, 0] - raman_tensors[:, 2, 2]) ** 2
+        + (raman_tensors[:, 1, 1] - raman_tensors[:, 2, 2]) ** 2
+        + 6.0 * (raman_tensors[:, 0, 1] ** 2 + raman_tensors[:, 0, 2] ** 2 + raman_tensors[:, 1, 2] ** 2)
+    ) / 2.0
+    intensities = 45.0 * alpha_squared + 7.0 * gamma_squared
+    if laser_correction:
+        laser_wavenumber = 10000000 / laser_wavelength
+        intensities *= get_laser_correction(phonon_wavenumbers, laser_wavenumber)
+    if bose_einstein_correction:
+        intensities *= get_bose_einstein_correction(phonon_wavenumbers, temperature)
+    return phonon_wavenumbers, intensities

@@ -6,15 +6,15 @@ Drop-in replacements for the three subsystems on the path
 implemented as hand-written CUDA behind the C-ABI in ``include/ramannoodle_b200.h``.
 """
 from .abstract import Dynamics, PolarizabilityModel, RamanSpectrum
-from .dynamics import Trajectory
+from .dynamics import Phonons, Trajectory
 from .exceptions import NativeLibraryError, UserError
 from .pmodel import ARTModel, InterpolationModel, accelerate
-from .spectrum import (MDRamanSpectrum, calc_signal_spectrum, convolve_spectrum,
+from .spectrum import (MDRamanSpectrum, PhononRamanSpectrum, calc_signal_spectrum, convolve_spectrum,
                        get_bose_einstein_correction, get_laser_correction)
 from .state import ModelState
 
 __all__ = [
     "ARTModel", "Dynamics", "InterpolationModel", "MDRamanSpectrum", "ModelState", "NativeLibraryError",
-    "PolarizabilityModel", "RamanSpectrum", "Trajectory", "UserError", "accelerate", "calc_signal_spectrum",
+    "Phonons", "PhononRamanSpectrum", "PolarizabilityModel", "RamanSpectrum", "Trajectory", "UserError", "accelerate", "calc_signal_spectrum",
     "convolve_spectrum", "get_bose_einstein_correction", "get_laser_correction",
 ]

@@ -16,7 +16,9 @@ import numpy as np
 from . import _lib
 from .abstract import Dynamics, PolarizabilityModel
 from .exceptions import get_type_error, verify_ndarray_shape
-from .spectrum import MDRamanSpectrum
+from .spectrum import MDRamanSpectrum, PhononRamanSpectrum
+
+RAMAN_TENSOR_CENTRAL_DIFFERENCE = 0.001  # ramannoodle/constants.py:248
 
 
 def _is_torch_tensor(obj) -> bool:
@@ -124,3 +126,43 @@ class Trajectory(Dynamics, Sequence):
                 raise IndexError("trajectory index out of bounds") from exc
             raise exc
         return item.cpu().numpy() if _is_torch_tensor(item) else item
+
+
+class Phonons(Dynamics):
+    """Harmonic lattice vibrations — drop-in for ``ramannoodle.dynamics.Phonons``
+    (``ramannoodle/dynamics/_phonon.py:13-108``).
+
+    The reference evaluates two S=1 batches per mode in a Python loop (``_phonon.py:93-106``);
+    here the 2·M central-difference geometries are stacked into ONE ``calc_polarizabilities``
+    call of shape (2M,N,3), so the whole phonon spectrum is a single kernel launch."""
+
+    def __init__(self, ref_positions, wavenumbers, displacements) -> None:
+        verify_ndarray_shape("ref_positions", ref_positions, (None, 3))
+        verify_ndarray_shape("wavenumbers", wavenumbers, (None,))
+        verify_ndarray_shape("displacements", displacements, (wavenumbers.size, ref_positions.shape[0], 3))
+        self._ref_positions = ref_positions
+        self._wavenumbers = wavenumbers
+        self._displacements = displacements
+
+    @property
+    def ref_positions(self) -> np.ndarray:
+        return self._ref_positions.copy()
+
+    @property
+    def wavenumbers(self) -> np.ndarray:
+        return self._wavenumbers.copy()
+
+    @property
+    def displacements(self) -> np.ndarray:
+        return self._displacements.copy()
+
+    def get_raman_spectrum(self, polarizability_model: PolarizabilityModel) -> PhononRamanSpectrum:
+        epsilon = self._displacements * RAMAN_TENSOR_CENTRAL_DIFFERENCE
+        batch = np.concatenate([self._ref_positions[None] + epsilon, self._ref_positions[None] - epsilon])
+        try:
+            polarizabilities = polarizability_model.calc_polarizabilities(batch)
+        except ValueError as exc:
+            raise ValueError("polarizability_model and phonons are incompatible") from exc
+        modes = self._wavenumbers.size
+        raman_tensors = (polarizabilities[:modes] - polarizabilities[modes:]) / RAMAN_TENSOR_CENTRAL_DIFFERENCE
+        return PhononRamanSpectrum(self._wavenumbers, np.asarray(raman_tensors))

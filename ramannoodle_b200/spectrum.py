@@ -196,6 +196,50 @@ class MDRamanSpectrum(RamanSpectrum):
         return wavenumbers.cpu().numpy(), intensities.cpu().numpy()
 
 
+class PhononRamanSpectrum(RamanSpectrum):
+    """Phonon-based first-order Raman spectrum (``ramannoodle/spectrum/_raman.py:72-194``).
+
+    ``measure`` is O(M) elementwise work on M = 3N Raman tensors (a few hundred numbers), so it
+    stays on the host with the reference's exact formulas; the data-parallel part of the phonon
+    path — the 2·M central-difference polarizabilities — is batched onto the GPU by
+    ``ramannoodle_b200.dynamics.Phonons.get_raman_spectrum``."""
+
+    def __init__(self, phonon_wavenumbers, raman_tensors) -> None:
+        verify_ndarray_shape("phonon_wavenumbers", phonon_wavenumbers, (None,))
+        verify_ndarray_shape("raman_tensors", raman_tensors, (len(phonon_wavenumbers), 3, 3))
+        self._phonon_wavenumbers = phonon_wavenumbers
+        self._raman_tensors = raman_tensors
+
+    @property
+    def phonon_wavenumbers(self) -> np.ndarray:
+        return self._phonon_wavenumbers.copy()
+
+    @property
+    def raman_tensors(self) -> np.ndarray:
+        return self._raman_tensors.copy()
+
+    # pylint: disable=too-many-arguments,too-many-positional-arguments
+    def measure(self, orientation="polycrystalline", laser_correction=False, laser_wavelength=522,
+                bose_einstein_correction=False, temperature=300):
+        if orientation != "polycrystalline":
+            raise NotImplementedError("only polycrystalline spectra are supported for now")
+        tensors = self._raman_tensors
+        alpha_squared = ((tensors[:, 0, 0] + tensors[:, 1, 1] + tensors[:, 2, 2]) / 3.0) ** 2
+        gamma_squared = (
+            (tensors[:, 0, 0] - tensors[:, 1, 1]) ** 2
+            + (tensors[:, 0, 0] - tensors[:, 2, 2]) ** 2
+            + (tensors[:, 1, 1] - tensors[:, 2, 2]) ** 2
+            + 6.0 * (tensors[:, 0, 1] ** 2 + tensors[:, 0, 2] ** 2 + tensors[:, 1, 2] ** 2)
+        ) / 2.0
+        intensities = 45.0 * alpha_squared + 7.0 * gamma_squared
+        if laser_correction:
+            laser_wavenumber = 10000000 / laser_wavelength
+            intensities *= get_laser_correction(self._phonon_wavenumbers, laser_wavenumber)
+        if bose_einstein_correction:
+            intensities *= get_bose_einstein_correction(self._phonon_wavenumbers, temperature)
+        return self._phonon_wavenumbers, intensities
+
+
 def calc_signal_spectrum(signal, sampling_rate: float):
     """Spectrum of one real signal (``ramannoodle/spectrum/utils.py:95-124``): the
     positive-frequency Fourier transform of its autocorrelation; ceil(S/2) points."""

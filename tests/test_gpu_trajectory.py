@@ -87,3 +87,26 @@ def test_trajectory_error_behaviour():
         rb.Trajectory(sto, [1, 2])
     with pytest.raises(ValueError, match=r"positions_ts has wrong shape: \(4,135\) != \(_,_,3\)"):
         rb.Trajectory(sto[:, :, 0], 1.0)
+
+
+def test_phonon_path_batched_on_gpu():
+    """Next row N1: the 2*M central-difference geometries of ``Phonons.get_raman_spectrum``
+    (dynamics/_phonon.py:93-106) as ONE batched GPU call, against the reference golden."""
+    from helpers import state_from_tables
+
+    with np.load(f"{GOLDEN}/phonons_tio2.npz") as ph, np.load(f"{GOLDEN}/real_tio2.npz") as data:
+        model = rb.InterpolationModel(state_from_tables(data, "k3"))
+        phonons = rb.Phonons(ph["ref_positions"], ph["wavenumbers"], ph["displacements"])
+        spectrum = phonons.get_raman_spectrum(model)
+        # Raman tensors are central differences of nearly equal polarizabilities (step 1e-3):
+        # the 1e-15 evaluation error is amplified by ~1e3 relative to the tensor scale
+        assert rel_err(spectrum.raman_tensors, ph["raman_tensors"]) <= 1e-9
+        wn, inten = spectrum.measure(laser_correction=True, laser_wavelength=532,
+                                     bose_einstein_correction=True, temperature=300)
+        assert np.array_equal(wn, ph["measure_wavenumbers"])
+        assert rel_err(inten, ph["measure_intensities"]) <= 1e-8
+        sto = rb.Phonons(np.zeros((5, 3)), np.ones(2), np.zeros((2, 5, 3)))
+        with pytest.raises(ValueError, match="polarizability_model and phonons are incompatible"):
+            sto.get_raman_spectrum(model)
+        with pytest.raises(ValueError, match=r"displacements has wrong shape: \(2,4,3\) != \(2,5,3\)"):
+            rb.Phonons(np.zeros((5, 3)), np.ones(2), np.zeros((2, 4, 3)))

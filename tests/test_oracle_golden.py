@@ -106,3 +106,16 @@ def test_apply_pbc(positions, known):
 def test_apply_pbc_displacement(displacement, known):
     """``test/tests/test_structure.py:216-230``."""
     assert np.allclose(ora.apply_pbc_displacement(displacement), known)
+
+
+def test_phonon_path_golden():
+    """Next row N1: ``Phonons.get_raman_spectrum`` + ``PhononRamanSpectrum.measure``
+    of the reference on TiO2 phonons x the P1 cubic model, replayed on the oracle."""
+    with np.load(f"{GOLDEN}/phonons_tio2.npz") as ph, np.load(f"{GOLDEN}/real_tio2.npz") as data:
+        model = oracle_model(state_from_tables(data, "k3"))
+        tensors = ora.phonon_raman_tensors(model, ph["ref_positions"], ph["displacements"])
+        assert np.array_equal(tensors, ph["raman_tensors"])
+        wn, inten = ora.phonon_measure(ph["wavenumbers"], tensors, laser_correction=True, laser_wavelength=532,
+                                       bose_einstein_correction=True, temperature=300)
+        assert np.array_equal(wn, ph["measure_wavenumbers"])
+        assert np.array_equal(inten, ph["measure_intensities"])

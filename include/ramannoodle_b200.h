@@ -156,6 +156,19 @@ int rn_convolve_spectrum(const double* d_wavenumbers, const double* d_intensitie
                          int kind, double width, const double* d_out_wavenumbers, int64_t num_out,
                          double* d_out_intensities, void* d_workspace, void* stream);
 
+/* Trajectory ingest — replaces the Python text parsing of io.vasp.xdatcar.read_positions_ts
+ * (ramannoodle/io/vasp/xdatcar.py:21-56; header/frames as io/vasp/poscar.py:_read_lattice,
+ * _read_atomic_symbols, _read_positions).  Host-only (no GPU needed): mmap + a thread pool
+ * running a correctly rounded decimal parser (values equal Python's float(token)).
+ * rn_xdatcar_scan returns the frame count, atom count and the scaled lattice (9 doubles, may
+ * be NULL); rn_xdatcar_read fills h_positions (S,N,3) — e.g. a pinned buffer — with the
+ * fractional coordinates as written, or wrapped into [0,1) like Trajectory.__init__
+ * (dynamics/trajectory.py:58) when wrap != 0 (num_threads <= 0: all cores).
+ * Direct-coordinate frames only. */
+int rn_xdatcar_scan(const char* path, int64_t* num_frames, int64_t* num_atoms, double* lattice);
+int rn_xdatcar_read(const char* path, double* h_positions, int64_t num_frames, int64_t num_atoms,
+                    int num_threads, int wrap);
+
 /* Page-lock / unlock a caller-owned host buffer (cudaHostRegister) for fast transfers. */
 int rn_host_register(void* h_ptr, size_t bytes);
 int rn_host_unregister(void* h_ptr);

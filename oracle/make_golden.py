@@ -9,6 +9,7 @@ Writes
   tests/golden/spectrum_cases.npz        reference measure()/calc_signal_spectrum outputs
   tests/golden/smearing.npz              the reference's own known_{gaussian,lorentzian}_spectrum goldens
   tests/golden/phonons_tio2.npz          Phonons.get_raman_spectrum / PhononRamanSpectrum.measure (next row N1)
+  tests/golden/sto_xdatcar*.{txt,npz}    the reference's XDATCAR fixture + its read_positions_ts output (next row N2)
 Everything here is produced by importing the reference through ``oracle/ref_bootstrap.py``
 (spglib/defusedxml stubbed; hot-path arithmetic untouched).  The GPU box has no reference
 tree: tests there read only these files.
@@ -217,6 +218,19 @@ def make_phonons() -> None:
     np.savez_compressed(os.path.join(GOLDEN, "phonons_tio2.npz"), **out)
 
 
+def make_ingest() -> None:
+    """Next row N2: the reference's own XDATCAR fixture (``test/data/STO/XDATCAR``, 4 frames x 135
+    atoms; copied as DATA) and what the reference reader makes of it
+    (``io/vasp/xdatcar.py:21-56``; pinned by the reference at ``test/tests/test_xdatcar.py``)."""
+    import shutil
+
+    from ramannoodle.io.vasp.xdatcar import read_positions_ts
+
+    src = os.path.join(REFERENCE_ROOT, "test/data/STO/XDATCAR")
+    shutil.copyfile(src, os.path.join(GOLDEN, "sto_xdatcar.txt"))
+    np.savez_compressed(os.path.join(GOLDEN, "sto_xdatcar_positions.npz"), positions_ts=read_positions_ts(src))
+
+
 def make_smearing() -> None:
     """The reference's own goldens for ``convolve_spectrum``
     (``test/tests/test_phonon_spectrum.py:403-449``)."""
@@ -238,6 +252,7 @@ def main() -> None:
     make_synthetic()
     make_spectrum()
     make_phonons()
+    make_ingest()
     for path in sorted(glob.glob(os.path.join(GOLDEN, "*.npz")) + glob.glob(os.path.join(DATA, "*.npz"))):
         print(f"{os.path.getsize(path):>9d}  {os.path.relpath(path, REPO)}")
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libramannoodle_b200.so")
-SOURCES = ["rn_model.cu", "rn_polarizability.cu", "rn_dense.cu", "rn_spectrum.cu", "rn_smear.cu"]
+SOURCES = ["rn_model.cu", "rn_polarizability.cu", "rn_dense.cu", "rn_spectrum.cu", "rn_smear.cu", "rn_ingest.cu"]
 HEADERS = [os.path.join(CSRC, "rn_common.cuh"), os.path.join(CSRC, "rn_device.cuh"), os.path.join(os.path.dirname(HERE), "include", "ramannoodle_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objects = list(pool.map(compile_one, SOURCES))
     if force or _stale(LIB, objects):
-        cmd = [nvcc, "-shared", "-o", LIB] + objects + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objects + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

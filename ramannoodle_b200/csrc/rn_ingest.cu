@@ -1,0 +1,406 @@
+// Trajectory ingest: VASP XDATCAR -> (S,N,3) fractional positions.
+//
+// The reference parses XDATCAR files line by line in Python (ramannoodle/io/vasp/xdatcar.py:21-56
+// through io/vasp/poscar.py:_read_lattice/_read_atomic_symbols/_read_positions); once the GPU
+// evaluates a million frames in under a millisecond, that text parsing is the end-to-end wall.
+// This is a host-side C++ reader: the file is mmap'ed, frame offsets are found in one pass over
+// the newlines, and frames are converted by a pool of threads with a correctly rounded decimal parser
+// (exact fast path + strtod fallback, matching Python's float()), straight into the caller's buffer
+// (e.g. pinned memory).
+// Semantics follow the reference reader: title line, scale factor, three lattice rows, symbols,
+// counts, then frames of one label line (first character D/d = direct) + N coordinate lines; the
+// series ends at the first blank/missing label line.  Cartesian frames are not supported here.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rn_common.cuh"
+
+namespace rn {
+
+struct MappedFile {
+    const char* data = nullptr;
+    size_t size = 0;
+    int fd = -1;
+    int64_t mtime_ns = 0;
+    ~MappedFile() {
+        if (data && size) munmap(const_cast<char*>(data), size);
+        if (fd >= 0) close(fd);
+    }
+    int open_path(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) {
+            set_error("cannot open %s: %s", path, strerror(errno));
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+        struct stat st;
+        if (fstat(fd, &st) != 0) {
+            set_error("cannot stat %s", path);
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+        size = (size_t)st.st_size;
+        mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+        if (size == 0) {
+            set_error("%s is empty", path);
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+        void* p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (p == MAP_FAILED) {
+            set_error("cannot mmap %s: %s", path, strerror(errno));
+            data = nullptr;
+            return RN_ERR_OUT_OF_MEMORY;
+        }
+        data = static_cast<const char*>(p);
+        return RN_OK;
+    }
+};
+
+// [begin, end) of the line starting at `pos` (end excludes the newline); returns the start of the next line
+static inline size_t next_line(const char* d, size_t size, size_t pos, size_t* end) {
+    const void* nl = (pos < size) ? memchr(d + pos, '\n', size - pos) : nullptr;
+    if (!nl) {
+        *end = size;
+        return size;
+    }
+    *end = (size_t)(static_cast<const char*>(nl) - d);
+    return *end + 1;
+}
+
+static inline const char* skip_space(const char* p, const char* e) {
+    while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) p++;
+    return p;
+}
+
+// One decimal number -> double, correctly rounded like Python's float().
+// Fast path (Clinger): up to 15 significant digits and |decimal exponent| <= 22 make both the
+// integer mantissa and the power of ten exact doubles, so ONE multiplication or division rounds
+// correctly.  Everything else (17-digit repr output, huge exponents, inf/nan) goes to glibc's
+// strtod, which is correctly rounded and thread-safe.  (libstdc++'s std::from_chars<double> takes a
+// process-wide lock in this toolchain and does not scale over threads.)
+static inline const char* parse_double(const char* p, const char* e, double* out) {
+    static const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                      1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    const char* start = p;
+    bool neg = false;
+    if (p < e && (*p == '-' || *p == '+')) {
+        neg = (*p == '-');
+        p++;
+    }
+    uint64_t mant = 0;
+    int digits = 0, exp10 = 0;
+    bool any = false, fast = true;
+    while (p < e && *p >= '0' && *p <= '9') {
+        any = true;
+        if (digits < 19) {
+            mant = mant * 10 + (uint64_t)(*p - '0');
+            if (mant) digits++;
+        } else {
+            fast = false;
+            exp10++;
+        }
+        p++;
+    }
+    if (p < e && *p == '.') {
+        p++;
+        while (p < e && *p >= '0' && *p <= '9') {
+            any = true;
+            if (digits < 19) {
+                mant = mant * 10 + (uint64_t)(*p - '0');
+                if (mant) digits++;
+                exp10--;
+            } else {
+                fast = false;
+            }
+            p++;
+        }
+    }
+    if (!any) {
+        fast = false;  // inf / nan / garbage: let strtod decide
+    } else if (p < e && (*p == 'e' || *p == 'E')) {
+        const char* q = p + 1;
+        bool eneg = false;
+        if (q < e && (*q == '-' || *q == '+')) {
+            eneg = (*q == '-');
+            q++;
+        }
+        if (q < e && *q >= '0' && *q <= '9') {
+            int ev = 0;
+            while (q < e && *q >= '0' && *q <= '9') {
+                if (ev < 10000) ev = ev * 10 + (*q - '0');
+                q++;
+            }
+            exp10 += eneg ? -ev : ev;
+            p = q;
+        }
+    }
+    if (fast && mant <= (1ull << 53) && exp10 >= -22 && exp10 <= 22) {
+        double v = (double)mant;
+        v = (exp10 < 0) ? v / kPow10[-exp10] : v * kPow10[exp10];
+        *out = neg ? -v : v;
+        return p;
+    }
+    // slow path: the token, NUL-terminated, through strtod
+    const char* tok_end = start;
+    while (tok_end < e && *tok_end != ' ' && *tok_end != '\t' && *tok_end != '\r') tok_end++;
+    char buf[128];
+    const size_t len = (size_t)(tok_end - start);
+    if (len == 0 || len >= sizeof(buf)) return nullptr;
+    memcpy(buf, start, len);
+    buf[len] = 0;
+    char* endp = nullptr;
+    const double v = strtod(buf, &endp);
+    if (endp == buf) return nullptr;
+    *out = v;
+    return start + (endp - buf);
+}
+
+// parse `count` whitespace-separated doubles from [p, e); returns false on failure
+static inline bool parse_doubles(const char* p, const char* e, int count, double* out) {
+    for (int i = 0; i < count; i++) {
+        p = skip_space(p, e);
+        const char* q = (p < e) ? parse_double(p, e, out + i) : nullptr;
+        if (!q) return false;
+        if (q < e && *q != ' ' && *q != '\t' && *q != '\r') return false;  // trailing garbage in the token
+        p = q;
+    }
+    return true;
+}
+
+struct XdatcarHeader {
+    double lattice[9];
+    int64_t num_atoms = 0;
+    size_t frames_begin = 0;  // byte offset of the first frame's label line
+};
+
+static int parse_header(const MappedFile& f, XdatcarHeader& h) {
+    size_t pos = 0, end = 0;
+    pos = next_line(f.data, f.size, pos, &end);  // title
+    size_t line = pos;
+    pos = next_line(f.data, f.size, pos, &end);
+    double scale = 0;
+    if (!parse_doubles(f.data + line, f.data + end, 1, &scale)) {
+        set_error("scale factor could not be parsed");
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    for (int r = 0; r < 3; r++) {
+        line = pos;
+        pos = next_line(f.data, f.size, pos, &end);
+        if (!parse_doubles(f.data + line, f.data + end, 3, h.lattice + 3 * r)) {
+            set_error("lattice could not be parsed");
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+        for (int c = 0; c < 3; c++) h.lattice[3 * r + c] *= scale;
+    }
+    // symbols line: count tokens
+    line = pos;
+    pos = next_line(f.data, f.size, pos, &end);
+    int symbols = 0;
+    for (const char* p = skip_space(f.data + line, f.data + end); p < f.data + end; p = skip_space(p, f.data + end)) {
+        symbols++;
+        while (p < f.data + end && *p != ' ' && *p != '\t' && *p != '\r') p++;
+    }
+    if (symbols == 0) {
+        set_error("no atom symbols found");
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    // counts line
+    line = pos;
+    pos = next_line(f.data, f.size, pos, &end);
+    int counts = 0;
+    int64_t atoms = 0;
+    for (const char* p = skip_space(f.data + line, f.data + end); p < f.data + end; p = skip_space(p, f.data + end)) {
+        int64_t v = 0;
+        auto res = std::from_chars(p, f.data + end, v);
+        if (res.ec != std::errc() || v < 0) {
+            set_error("could not parse ion counts");
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+        atoms += v;
+        counts++;
+        p = res.ptr;
+    }
+    if (counts != symbols) {
+        set_error("wrong number of ion counts: %d != %d", counts, symbols);
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    if (atoms <= 0) {
+        set_error("no atoms in file");
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    h.num_atoms = atoms;
+    h.frames_begin = pos;
+    return RN_OK;
+}
+
+// offsets of the first coordinate line of every frame
+static int scan_frames(const MappedFile& f, const XdatcarHeader& h, std::vector<size_t>& starts) {
+    size_t pos = h.frames_begin, end = 0;
+    while (pos < f.size) {
+        const size_t label = pos;
+        pos = next_line(f.data, f.size, pos, &end);
+        const char* p = f.data + label;
+        const char* e = f.data + end;
+        // the reference stops at a label line that is empty or starts with whitespace
+        if (p >= e || *p == ' ' || *p == '\t' || *p == '\r') break;
+        char c = *p;
+        if (c == 's' || c == 'S') {  // selective dynamics: the coordinate format is on the next line
+            const size_t l2 = pos;
+            pos = next_line(f.data, f.size, pos, &end);
+            if (l2 >= f.size) break;
+            c = f.data[l2];
+        }
+        if (c == 'c' || c == 'C') {
+            set_error("Cartesian XDATCAR frames are not supported by the fast reader");
+            return RN_ERR_UNSUPPORTED;
+        }
+        if (c != 'd' && c != 'D') {
+            set_error("unrecognized coordinate format in frame %zu", starts.size() + 1);
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+        starts.push_back(pos);
+        for (int64_t a = 0; a < h.num_atoms; a++) {
+            if (pos >= f.size) {
+                set_error("positions could not be parsed: file ends inside frame %zu", starts.size());
+                return RN_ERR_INVALID_ARGUMENT;
+            }
+            pos = next_line(f.data, f.size, pos, &end);
+        }
+    }
+    return RN_OK;
+}
+
+// rn_xdatcar_scan is always followed by rn_xdatcar_read on the same file: keep the last frame index
+// so the newline pass runs once (keyed by path, size and mtime).
+struct FrameIndex {
+    std::string path;
+    size_t size = 0;
+    int64_t mtime_ns = 0;
+    XdatcarHeader header;
+    std::vector<size_t> starts;
+};
+static std::mutex g_index_mutex;
+static FrameIndex g_index;
+
+static int index_file(const char* path, const MappedFile& f, XdatcarHeader& h, std::vector<size_t>& starts,
+                      bool consume) {
+    {
+        std::lock_guard<std::mutex> lock(g_index_mutex);
+        if (g_index.path == path && g_index.size == f.size && g_index.mtime_ns == f.mtime_ns &&
+            !g_index.starts.empty()) {
+            h = g_index.header;
+            if (consume) {
+                starts.swap(g_index.starts);
+                g_index.path.clear();
+            } else {
+                starts = g_index.starts;
+            }
+            return RN_OK;
+        }
+    }
+    int rc = parse_header(f, h);
+    if (rc != RN_OK) return rc;
+    rc = scan_frames(f, h, starts);
+    if (rc != RN_OK) return rc;
+    if (!consume) {
+        std::lock_guard<std::mutex> lock(g_index_mutex);
+        g_index.path = path;
+        g_index.size = f.size;
+        g_index.mtime_ns = f.mtime_ns;
+        g_index.header = h;
+        g_index.starts = starts;
+    }
+    return RN_OK;
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+// ramannoodle/io/vasp/xdatcar.py:21-56 (header + frame count); lattice rows are scaled lattice vectors.
+extern "C" int rn_xdatcar_scan(const char* path, int64_t* num_frames, int64_t* num_atoms, double* lattice) {
+    RN_CHECK_ARG(path && num_frames && num_atoms, "null pointer");
+    MappedFile f;
+    int rc = f.open_path(path);
+    if (rc != RN_OK) return rc;
+    XdatcarHeader h;
+    std::vector<size_t> starts;
+    rc = index_file(path, f, h, starts, false);
+    if (rc != RN_OK) return rc;
+    *num_frames = (int64_t)starts.size();
+    *num_atoms = h.num_atoms;
+    if (lattice) memcpy(lattice, h.lattice, sizeof(h.lattice));
+    return RN_OK;
+}
+
+// Fills h_positions (num_frames, num_atoms, 3) with the fractional coordinates as written, or —
+// wrap != 0 — wrapped into [0,1) as x - floor(x), which is what Trajectory.__init__ applies
+// (ramannoodle/dynamics/trajectory.py:58, structure/structure_utils.py:apply_pbc).
+// num_frames / num_atoms must match rn_xdatcar_scan.  num_threads <= 0: all cores.
+extern "C" int rn_xdatcar_read(const char* path, double* h_positions, int64_t num_frames, int64_t num_atoms,
+                               int num_threads, int wrap) {
+    RN_CHECK_ARG(path && h_positions, "null pointer");
+    MappedFile f;
+    int rc = f.open_path(path);
+    if (rc != RN_OK) return rc;
+    XdatcarHeader h;
+    std::vector<size_t> starts;
+    rc = index_file(path, f, h, starts, true);
+    if (rc != RN_OK) return rc;
+    RN_CHECK_ARG((int64_t)starts.size() == num_frames && h.num_atoms == num_atoms,
+                 "file holds %zu frames of %lld atoms, buffer was sized for %lld x %lld", starts.size(),
+                 (long long)h.num_atoms, (long long)num_frames, (long long)num_atoms);
+    if (num_threads <= 0) num_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    num_threads = (int)std::min<int64_t>(num_threads, std::max<int64_t>(1, num_frames));
+    std::atomic<int64_t> bad_frame{-1};
+    auto convert = [&](int64_t f0, int64_t f1) {
+        for (int64_t fr = f0; fr < f1 && bad_frame.load(std::memory_order_relaxed) < 0; fr++) {
+            size_t pos = starts[(size_t)fr], end = 0;
+            double* out = h_positions + fr * num_atoms * 3;
+            for (int64_t a = 0; a < num_atoms; a++) {
+                const size_t line = pos;
+                pos = next_line(f.data, f.size, pos, &end);
+                if (!parse_doubles(f.data + line, f.data + end, 3, out + 3 * a)) {
+                    bad_frame.store(fr);
+                    return;
+                }
+                if (wrap) {
+                    for (int c = 0; c < 3; c++) out[3 * a + c] -= floor(out[3 * a + c]);
+                }
+            }
+        }
+    };
+    if (num_threads == 1) {
+        convert(0, num_frames);
+    } else {
+        // frames are handed out in small blocks so a descheduled thread does not hold up the rest
+        const int64_t block = std::max<int64_t>(1, std::min<int64_t>(64, num_frames / (8 * num_threads)));
+        std::atomic<int64_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const int64_t f0 = next.fetch_add(block);
+                if (f0 >= num_frames) return;
+                convert(f0, std::min<int64_t>(num_frames, f0 + block));
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < num_threads; t++) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+    }
+    if (bad_frame.load() >= 0) {
+        set_error("positions could not be parsed in frame %lld", (long long)bad_frame.load() + 1);
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    return RN_OK;
+}

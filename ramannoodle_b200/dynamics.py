@@ -51,6 +51,20 @@ class Trajectory(Dynamics, Sequence):
         else:
             self._positions_ts = self._wrap_host(np.asarray(positions_ts), pin_memory)
 
+    @classmethod
+    def _from_wrapped(cls, positions: np.ndarray, timestep: float, pinned_owner=None) -> "Trajectory":
+        """Adopts host positions that are already wrapped into [0,1) (``io.read_trajectory`` parses
+        straight into a page-locked buffer) without another pass over them."""
+        verify_ndarray_shape("positions_ts", positions, (None, None, 3))
+        self = cls.__new__(cls)
+        timestep = float(timestep)
+        if timestep <= 0:
+            raise ValueError("timestep must be positive")
+        self._timestep = timestep
+        self._pinned_owner = pinned_owner
+        self._positions_ts = positions
+        return self
+
     @staticmethod
     def _wrap_device(tensor):
         import torch  # pylint: disable=import-outside-toplevel

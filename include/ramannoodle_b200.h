@@ -112,6 +112,20 @@ int rn_calc_polarizabilities_host_multi(const rn_model* model, const double* h_p
                                         int64_t num_frames, double* const* d_alpha_outputs,
                                         int num_outputs, int64_t chunk_frames);
 
+/* Mask sweeps: num_models models of ONE structure — in practice the
+ * get_masked_model copies of a model (pmodel/_interpolation.py:697-708; ARTModel.get_dof_indexes,
+ * pmodel/_art.py:335-365), which differ only in `weight` — evaluated on the same positions;
+ * d_alpha_outputs[g] (num_frames*9 doubles, device) receives exactly what
+ * rn_calc_polarizabilities(models[g], ...) writes.  Runs of up to four purely linear models
+ * (every ARTModel) share one kernel: the trajectory is read and wrapped once and contracted with
+ * the stacked (3N x 9G) table.  The host form streams h_positions across PCIe once for all models. */
+int rn_calc_polarizabilities_sweep(const rn_model* const* models, int num_models,
+                                   const double* d_positions, int64_t num_frames,
+                                   double* const* d_alpha_outputs, void* stream);
+int rn_calc_polarizabilities_host_sweep(const rn_model* const* models, int num_models,
+                                        const double* h_positions, int64_t num_frames,
+                                        double* const* d_alpha_outputs, int64_t chunk_frames);
+
 /* Trajectory.__init__ stores apply_pbc(positions_ts) (dynamics/_trajectory.py:45;
  * structure/utils.py:27: p - p // 1).  Elementwise, in place allowed (d_out == d_in). */
 int rn_apply_pbc(const double* d_in, double* d_out, int64_t count, void* stream);

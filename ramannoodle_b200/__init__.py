@@ -8,7 +8,7 @@ implemented as hand-written CUDA behind the C-ABI in ``include/ramannoodle_b200.
 from .abstract import Dynamics, PolarizabilityModel, RamanSpectrum
 from .dynamics import Phonons, Trajectory
 from .exceptions import NativeLibraryError, UserError
-from .pmodel import ARTModel, InterpolationModel, accelerate
+from .pmodel import ARTModel, InterpolationModel, accelerate, calc_polarizabilities_sweep
 from .spectrum import (MDRamanSpectrum, PhononRamanSpectrum, calc_signal_spectrum, convolve_spectrum,
                        get_bose_einstein_correction, get_laser_correction)
 from .state import ModelState

@@ -68,6 +68,7 @@ struct rn_model {
     int dense_degree = 0;    // max degree over dense DOFs (piece records are padded to it)
     int dense_max_pieces = 0;
     double alpha0[9] = {0};  // ref_polarizability + constant parts of the linear DOFs
+    uint64_t ref_hash = 0;   // FNV-1a of the reference positions and lattice bytes (mask sweeps group on it)
 
     // device tables (all fp64)
     double* d_ref_wrapped = nullptr;  // (K)   apply_pbc(ref positions)

@@ -213,6 +213,16 @@ extern "C" int rn_model_create(const double* h_ref_positions, int64_t num_atoms,
     m->num_dofs = num_dofs;
     const int64_t K = m->dim;
     const bool force_dense = (flags & RN_MODEL_FORCE_DENSE) != 0;
+    {
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&h](const double* data, size_t count) {
+            const unsigned char* bytes = reinterpret_cast<const unsigned char*>(data);
+            for (size_t i = 0; i < count * sizeof(double); i++) h = (h ^ bytes[i]) * 1099511628211ull;
+        };
+        mix(h_ref_positions, (size_t)K);
+        mix(h_lattice, 9);
+        m->ref_hash = h;
+    }
 
     // ---- splines -> piecewise polynomials; classify linear vs dense ----
     std::vector<PiecewisePoly> pps((size_t)num_dofs);

@@ -129,6 +129,19 @@ class Trajectory(Dynamics, Sequence):
             raise ValueError("polarizability_model and trajectory are incompatible") from exc
         return MDRamanSpectrum(polarizability_ts, self._timestep)
 
+    def get_raman_spectra(self, polarizability_models) -> list:
+        """Mask sweep: one ``MDRamanSpectrum`` per model, all evaluated in a
+        single pass over the trajectory (``pmodel.calc_polarizabilities_sweep``).  Equivalent to
+        ``[self.get_raman_spectrum(m) for m in polarizability_models]``, which is how the
+        reference evaluates ``get_masked_model`` copies (``_interpolation.py:697-708``)."""
+        from .pmodel import calc_polarizabilities_sweep  # pylint: disable=import-outside-toplevel
+
+        try:
+            series = calc_polarizabilities_sweep(polarizability_models, self._positions_ts, to_device=True)
+        except ValueError as exc:
+            raise ValueError("polarizability_model and trajectory are incompatible") from exc
+        return [MDRamanSpectrum(series[g], self._timestep) for g in range(series.shape[0])]
+
     def __len__(self) -> int:
         return int(self._positions_ts.shape[0])
 

@@ -134,6 +134,20 @@ class InterpolationModel(PolarizabilityModel):
         result.mask = new_mask
         return result
 
+    def calc_polarizabilities_masked(self, positions_batch, masks, to_device: bool = False):
+        """Polarizabilities ``(G,S,3,3)`` of this model under each of the ``G`` masks (rows of a
+        ``(G,J)`` bool array; True = DOF masked, as the ``mask`` property) in one pass over
+        ``positions_batch`` — what evaluating ``G`` ``get_masked_model`` copies returns."""
+        masks = np.asarray(masks)
+        if masks.ndim != 2 or masks.shape[1] != self._state.mask.shape[0]:
+            raise get_shape_error("masks", masks, f"(_,{self._state.mask.shape[0]})")
+        copies = []
+        for row in masks:
+            clone = copy.deepcopy(self)
+            clone.mask = np.asarray(row, dtype=bool)
+            copies.append(clone)
+        return calc_polarizabilities_sweep(copies, positions_batch, to_device=to_device)
+
     def __deepcopy__(self, memo):
         clone = type(self)(copy.deepcopy(self._state, memo), device=self._device, force_dense=self._force_dense)
         return clone
@@ -291,6 +305,64 @@ class InterpolationModel(PolarizabilityModel):
                            ctypes.c_void_p(alpha.data_ptr()), stream)
         _lib.check(status, "rn_calc_polarizabilities" if wrap else "rn_get_polarizability")
         return alpha
+
+
+def calc_polarizabilities_sweep(models, positions_batch, to_device: bool = False):
+    """Evaluate several models of ONE structure (typically ``get_masked_model`` copies,
+    ``_interpolation.py:697-708``) on the same positions in one pass: returns ``(G,S,3,3)``.
+
+    A host trajectory crosses PCIe once; purely linear models (every ``ARTModel``) are contracted
+    together by one kernel (``rn_calc_polarizabilities_sweep``), other models run one after the other
+    on the resident positions.  Each slice equals ``models[g].calc_polarizabilities(positions_batch)``.
+    numpy in -> numpy out (a CUDA tensor if ``to_device``); CUDA tensor in -> CUDA tensor out."""
+    import torch  # pylint: disable=import-outside-toplevel
+
+    models = list(models)
+    if len(models) == 0:
+        raise ValueError("at least one model is required")
+    if len(models) > 64:
+        raise ValueError("at most 64 models per sweep")
+    for model in models:
+        if not isinstance(model, InterpolationModel):
+            raise get_type_error("models", model, "InterpolationModel")
+    num_atoms = models[0].num_atoms
+    if any(model.num_atoms != num_atoms for model in models):
+        raise ValueError("models of a sweep must describe the same structure")
+    is_tensor = _is_torch_tensor(positions_batch)
+    if is_tensor:
+        if not positions_batch.is_cuda:
+            raise get_type_error("positions", positions_batch, "ndarray or CUDA tensor")
+    elif not isinstance(positions_batch, np.ndarray):
+        raise get_type_error("positions", positions_batch, "ndarray")
+    if positions_batch.ndim != 3 or tuple(positions_batch.shape[1:]) != (num_atoms, 3):
+        raise get_shape_error("positions", positions_batch, f"(_,{num_atoms},3)")
+    for model in models:
+        model._check_dummy()  # pylint: disable=protected-access
+    count = len(models)
+    num_frames = int(positions_batch.shape[0])
+    if is_tensor:
+        data = positions_batch.to(torch.float64).contiguous()
+        device = models[0]._resolve_device(data)  # pylint: disable=protected-access
+    else:
+        data = np.ascontiguousarray(positions_batch, dtype=np.float64)
+        device = models[0]._resolve_device()  # pylint: disable=protected-access
+    natives = [model._native_model(device) for model in models]  # pylint: disable=protected-access
+    handles = (ctypes.c_void_p * count)(*[native.handle for native in natives])
+    with torch.cuda.device(device):
+        alpha = torch.empty((count, num_frames, 3, 3), dtype=torch.float64, device=f"cuda:{device}")
+        if num_frames == 0:
+            return alpha if (is_tensor or to_device) else alpha.cpu().numpy()
+        outputs = (ctypes.c_void_p * count)(*[ctypes.c_void_p(alpha[g].data_ptr()) for g in range(count)])
+        if is_tensor:
+            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            status = _lib.lib().rn_calc_polarizabilities_sweep(handles, count, ctypes.c_void_p(data.data_ptr()),
+                                                               num_frames, outputs, stream)
+            _lib.check(status, "rn_calc_polarizabilities_sweep")
+            return alpha
+        torch.cuda.synchronize(device)
+        status = _lib.lib().rn_calc_polarizabilities_host_sweep(handles, count, _ptr(data), num_frames, outputs, 0)
+        _lib.check(status, "rn_calc_polarizabilities_host_sweep")
+    return alpha if to_device else alpha.cpu().numpy()
 
 
 class ARTModel(InterpolationModel):

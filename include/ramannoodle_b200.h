@@ -183,6 +183,19 @@ int rn_xdatcar_scan(const char* path, int64_t* num_frames, int64_t* num_atoms, d
 int rn_xdatcar_read(const char* path, double* h_positions, int64_t num_frames, int64_t num_atoms,
                     int num_threads, int wrap);
 
+/* OUTCAR molecular-dynamics trajectories — replaces the line-by-line Python parsing of
+ * io.vasp.outcar.read_trajectory (ramannoodle/io/vasp/outcar.py:497-538; header fields as
+ * :46-86 atom count, :481-494 timestep, :212-241 lattice; ML/ab-initio step rule :520-527).
+ * rn_outcar_scan returns the number of kept frames, the atom count, the lattice (9 doubles, rows are
+ * lattice vectors, may be NULL) and the timestep in fs (may be NULL).  rn_outcar_read fills
+ * h_positions (S,N,3): the Cartesian coordinates as written when inv_lattice is NULL, else
+ * cart @ inv_lattice (row-major 3x3, the reference's np.linalg.inv(lattice)), wrapped into [0,1)
+ * when wrap != 0.  Host-only. */
+int rn_outcar_scan(const char* path, int64_t* num_frames, int64_t* num_atoms, double* lattice,
+                   double* timestep_fs);
+int rn_outcar_read(const char* path, double* h_positions, int64_t num_frames, int64_t num_atoms,
+                   const double* inv_lattice, int num_threads, int wrap);
+
 /* Page-lock / unlock a caller-owned host buffer (cudaHostRegister) for fast transfers. */
 int rn_host_register(void* h_ptr, size_t bytes);
 int rn_host_unregister(void* h_ptr);

@@ -230,6 +230,21 @@ def make_ingest() -> None:
     shutil.copyfile(src, os.path.join(GOLDEN, "sto_xdatcar.txt"))
     np.savez_compressed(os.path.join(GOLDEN, "sto_xdatcar_positions.npz"), positions_ts=read_positions_ts(src))
 
+    # OUTCAR molecular-dynamics fixture (``test/data/LLZO/OUTCAR_trajectory``: 15 kept frames x 108
+    # atoms, machine-learned + ab-initio steps; pinned by ``test/tests/test_outcar.py:76-94``),
+    # gzip-compressed DATA copy, and the reference reader's output (``io/vasp/outcar.py:497-538``)
+    import gzip
+
+    from ramannoodle.io.vasp.outcar import read_trajectory
+
+    src = os.path.join(REFERENCE_ROOT, "test/data/LLZO/OUTCAR_trajectory")
+    with open(src, "rb") as fin, gzip.GzipFile(os.path.join(GOLDEN, "llzo_outcar_trajectory.txt.gz"), "wb",
+                                               mtime=0) as fout:
+        shutil.copyfileobj(fin, fout)
+    trajectory = read_trajectory(src)
+    np.savez_compressed(os.path.join(GOLDEN, "llzo_outcar_trajectory.npz"), positions_ts=trajectory.positions_ts,
+                        timestep=trajectory.timestep)
+
 
 def make_smearing() -> None:
     """The reference's own goldens for ``convolve_spectrum``

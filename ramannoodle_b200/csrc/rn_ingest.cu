@@ -280,6 +280,201 @@ static int scan_frames(const MappedFile& f, const XdatcarHeader& h, std::vector<
     return RN_OK;
 }
 
+// ---- OUTCAR molecular-dynamics trajectories (ramannoodle/io/vasp/outcar.py:497-538) ----------
+//
+// The reference walks the file once, front to back: POTCAR block -> "ions per type" (atom count,
+// :46-86), "time-step for ionic-motion" (:481-494), "Write flags" then "direct lattice vectors"
+// (:212-241), then every "POSITION ... TOTAL-FORCE" block: one separator line and N lines whose
+// first three numbers are Cartesian coordinates.  With machine-learned force fields an ab-initio
+// block that directly follows an "(ML)" block repeats the same step and is skipped (:520-527).
+
+struct OutcarHeader {
+    int64_t num_atoms = 0;
+    double timestep = 0.0;
+    double lattice[9];
+    size_t frames_begin = 0;
+};
+
+// first line at or after `pos` that contains `needle`: [line, end) and the start of the next line
+static bool find_line(const MappedFile& f, size_t pos, const char* needle, size_t* line, size_t* end, size_t* next) {
+    if (pos >= f.size) return false;
+    const void* hit = memmem(f.data + pos, f.size - pos, needle, strlen(needle));
+    if (!hit) return false;
+    size_t at = (size_t)(static_cast<const char*>(hit) - f.data);
+    size_t b = at;
+    while (b > pos && f.data[b - 1] != '\n') b--;
+    *line = b;
+    *next = next_line(f.data, f.size, b, end);
+    return true;
+}
+
+static bool line_contains(const MappedFile& f, size_t line, size_t end, const char* needle) {
+    return memmem(f.data + line, end - line, needle, strlen(needle)) != nullptr;
+}
+
+static const char* const kElementSymbols[] = {
+    "H",  "He", "Li", "Be", "B",  "C",  "N",  "O",  "F",  "Ne", "Na", "Mg", "Al", "Si", "P",  "S",  "Cl", "Ar", "K",  "Ca",
+    "Sc", "Ti", "V",  "Cr", "Mn", "Fe", "Co", "Ni", "Cu", "Zn", "Ga", "Ge", "As", "Se", "Br", "Kr", "Rb", "Sr", "Y",  "Zr",
+    "Nb", "Mo", "Tc", "Ru", "Rh", "Pd", "Ag", "Cd", "In", "Sn", "Sb", "Te", "I",  "Xe", "Cs", "Ba", "La", "Ce", "Pr", "Nd",
+    "Pm", "Sm", "Eu", "Gd", "Tb", "Dy", "Ho", "Er", "Tm", "Yb", "Lu", "Hf", "Ta", "W",  "Re", "Os", "Ir", "Pt", "Au", "Hg",
+    "Tl", "Pb", "Bi", "Po", "At", "Rn", "Fr", "Ra", "Ac", "Th", "Pa", "U",  "Np", "Pu", "Am", "Cm", "Bk", "Cf", "Es", "Fm",
+    "Md", "No", "Lr", "Rf", "Db", "Sg", "Bh", "Hs", "Mt", "Ds", "Rg", "Cn", "Nh", "Fl", "Mc", "Lv", "Ts", "Og"};
+
+// outcar.py:27-43: second-to-last token of a POTCAR line, cut at '_', must be an element symbol
+static bool potcar_symbol_ok(const MappedFile& f, size_t line, size_t end) {
+    const char* toks[64];
+    size_t lens[64];
+    int count = 0;
+    const char* p = f.data + line;
+    const char* e = f.data + end;
+    while (p < e) {
+        p = skip_space(p, e);
+        if (p >= e) break;
+        const char* b = p;
+        while (p < e && *p != ' ' && *p != '\t' && *p != '\r') p++;
+        if (count < 64) {
+            toks[count] = b;
+            lens[count] = (size_t)(p - b);
+            count++;
+        }
+    }
+    if (count < 2) return false;
+    const char* tok = toks[count - 2];
+    size_t len = lens[count - 2];
+    for (size_t i = 0; i < len; i++)
+        if (tok[i] == '_') len = i;
+    for (const char* sym : kElementSymbols)
+        if (strlen(sym) == len && memcmp(sym, tok, len) == 0) return true;
+    return false;
+}
+
+static int parse_outcar_header(const MappedFile& f, OutcarHeader& h) {
+    size_t line = 0, end = 0, pos = 0;
+    if (!find_line(f, 0, "POTCAR:    ", &line, &end, &pos)) {
+        set_error("POTCAR block not found");
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    int symbols = 0;
+    for (;;) {
+        if (!potcar_symbol_ok(f, line, end)) {
+            set_error("POTCAR block could not be parsed");
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+        symbols++;
+        if (pos >= f.size) break;
+        line = pos;
+        pos = next_line(f.data, f.size, pos, &end);
+        if (!line_contains(f, line, end, "POTCAR")) break;
+    }
+    if (pos < f.size) {  // the line after the block: a VRHFIN line means the block listed one entry twice
+        line = pos;
+        pos = next_line(f.data, f.size, pos, &end);
+        if (line_contains(f, line, end, "VRHFIN")) symbols--;
+    }
+    if (!find_line(f, pos, "ions per type", &line, &end, &pos)) {
+        set_error("ion number block could not be parsed");
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    {
+        int token = 0, used = 0;
+        int64_t atoms = 0;
+        const char* p = f.data + line;
+        const char* e = f.data + end;
+        while (p < e) {
+            p = skip_space(p, e);
+            if (p >= e) break;
+            const char* b = p;
+            while (p < e && *p != ' ' && *p != '\t' && *p != '\r') p++;
+            if (token >= 4) {
+                int64_t v = 0;
+                auto res = std::from_chars(b, p, v);
+                if (res.ec != std::errc() || res.ptr != p) {
+                    set_error("ion number block could not be parsed");
+                    return RN_ERR_INVALID_ARGUMENT;
+                }
+                if (used < symbols) atoms += v;  // zip(potcar_symbols, atomic_numbers)
+                used++;
+            }
+            token++;
+        }
+        if (atoms <= 0) {
+            set_error("ion number block could not be parsed");
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+        h.num_atoms = atoms;
+    }
+    if (!find_line(f, pos, "time-step for ionic-motion", &line, &end, &pos)) {
+        set_error("timestep not found");
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    {
+        const char* p = f.data + line;
+        const char* e = f.data + end;
+        const char* tok = nullptr;
+        const char* tok_end = nullptr;
+        for (int t = 0; t < 3; t++) {
+            p = skip_space(p, e);
+            tok = p;
+            while (p < e && *p != ' ' && *p != '\t' && *p != '\r') p++;
+            tok_end = p;
+        }
+        double v = 0;
+        if (!tok || tok == tok_end || parse_double(tok, tok_end, &v) != tok_end) {
+            set_error("timestep could not be parsed");
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+        h.timestep = v;
+    }
+    if (!find_line(f, pos, "Write flags", &line, &end, &pos) ||
+        !find_line(f, pos, "direct lattice vectors      ", &line, &end, &pos)) {
+        set_error("outcar does not have expected format");
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    for (int r = 0; r < 3; r++) {
+        if (pos >= f.size) {
+            set_error("lattice could not be parsed");
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+        line = pos;
+        pos = next_line(f.data, f.size, pos, &end);
+        if (!parse_doubles(f.data + line, f.data + end, 3, h.lattice + 3 * r)) {
+            set_error("lattice could not be parsed");
+            return RN_ERR_INVALID_ARGUMENT;
+        }
+    }
+    h.frames_begin = pos;
+    return RN_OK;
+}
+
+// offsets of the first coordinate line of every frame the reference keeps
+static int scan_outcar_frames(const MappedFile& f, const OutcarHeader& h, std::vector<size_t>& starts) {
+    static const char kBlock[] = "POSITION                                       TOTAL-FORCE ";
+    size_t pos = h.frames_begin, line = 0, end = 0;
+    bool ml_step = false;
+    while (find_line(f, pos, kBlock, &line, &end, &pos)) {
+        const bool is_ml = line_contains(f, line, end, "(ML)");
+        if (ml_step && !is_ml) {  // ab-initio repeat of the ML step just read
+            ml_step = false;
+            continue;
+        }
+        ml_step = is_ml;
+        if (pos < f.size) pos = next_line(f.data, f.size, pos, &end);  // separator line
+        starts.push_back(pos);
+        for (int64_t a = 0; a < h.num_atoms; a++) {
+            if (pos >= f.size) {
+                set_error("Cartesian positions could not be parsed: file ends inside frame %zu", starts.size());
+                return RN_ERR_INVALID_ARGUMENT;
+            }
+            pos = next_line(f.data, f.size, pos, &end);
+        }
+    }
+    if (starts.empty()) {
+        set_error("no trajectory found");
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    return RN_OK;
+}
+
 // rn_xdatcar_scan is always followed by rn_xdatcar_read on the same file: keep the last frame index
 // so the newline pass runs once (keyed by path, size and mtime).
 struct FrameIndex {
@@ -400,6 +595,83 @@ extern "C" int rn_xdatcar_read(const char* path, double* h_positions, int64_t nu
     }
     if (bad_frame.load() >= 0) {
         set_error("positions could not be parsed in frame %lld", (long long)bad_frame.load() + 1);
+        return RN_ERR_INVALID_ARGUMENT;
+    }
+    return RN_OK;
+}
+
+// ramannoodle/io/vasp/outcar.py:497-538 (read_trajectory): frame count, atom count, lattice (rows
+// are lattice vectors, Angstrom) and the timestep (fs) of an OUTCAR molecular-dynamics run.
+extern "C" int rn_outcar_scan(const char* path, int64_t* num_frames, int64_t* num_atoms, double* lattice,
+                              double* timestep_fs) {
+    RN_CHECK_ARG(path && num_frames && num_atoms, "null pointer");
+    MappedFile f;
+    int rc = f.open_path(path);
+    if (rc != RN_OK) return rc;
+    OutcarHeader h;
+    rc = parse_outcar_header(f, h);
+    if (rc != RN_OK) return rc;
+    std::vector<size_t> starts;
+    rc = scan_outcar_frames(f, h, starts);
+    if (rc != RN_OK) return rc;
+    *num_frames = (int64_t)starts.size();
+    *num_atoms = h.num_atoms;
+    if (lattice) memcpy(lattice, h.lattice, sizeof(h.lattice));
+    if (timestep_fs) *timestep_fs = h.timestep;
+    return RN_OK;
+}
+
+// Fills h_positions (num_frames, num_atoms, 3).  inv_lattice == NULL: the Cartesian coordinates as
+// written.  Otherwise fractional coordinates cart @ inv_lattice (row-major 3x3, what
+// outcar.py:529 computes per frame), wrapped into [0,1) when wrap != 0.
+extern "C" int rn_outcar_read(const char* path, double* h_positions, int64_t num_frames, int64_t num_atoms,
+                              const double* inv_lattice, int num_threads, int wrap) {
+    RN_CHECK_ARG(path && h_positions, "null pointer");
+    MappedFile f;
+    int rc = f.open_path(path);
+    if (rc != RN_OK) return rc;
+    OutcarHeader h;
+    rc = parse_outcar_header(f, h);
+    if (rc != RN_OK) return rc;
+    std::vector<size_t> starts;
+    rc = scan_outcar_frames(f, h, starts);
+    if (rc != RN_OK) return rc;
+    RN_CHECK_ARG((int64_t)starts.size() == num_frames && h.num_atoms == num_atoms,
+                 "file holds %zu frames of %lld atoms, buffer was sized for %lld x %lld", starts.size(),
+                 (long long)h.num_atoms, (long long)num_frames, (long long)num_atoms);
+    if (num_threads <= 0) num_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    num_threads = (int)std::min<int64_t>(num_threads, std::max<int64_t>(1, num_frames));
+    std::atomic<int64_t> bad_frame{-1};
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const int64_t fr = next.fetch_add(1);
+            if (fr >= num_frames || bad_frame.load(std::memory_order_relaxed) >= 0) return;
+            size_t pos = starts[(size_t)fr], end = 0;
+            double* out = h_positions + fr * num_atoms * 3;
+            for (int64_t a = 0; a < num_atoms; a++) {
+                const size_t line = pos;
+                pos = next_line(f.data, f.size, pos, &end);
+                double c[3];
+                if (!parse_doubles(f.data + line, f.data + end, 3, c)) {
+                    bad_frame.store(fr);
+                    return;
+                }
+                for (int j = 0; j < 3; j++) {
+                    double v = c[j];
+                    if (inv_lattice) v = c[0] * inv_lattice[j] + c[1] * inv_lattice[3 + j] + c[2] * inv_lattice[6 + j];
+                    if (inv_lattice && wrap) v -= floor(v);
+                    out[3 * a + j] = v;
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < num_threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    if (bad_frame.load() >= 0) {
+        set_error("Cartesian positions could not be parsed in frame %lld", (long long)bad_frame.load() + 1);
         return RN_ERR_INVALID_ARGUMENT;
     }
     return RN_OK;

@@ -115,7 +115,115 @@ def test_malformed_files(tmp_path):
     with pytest.raises(FileNotFoundError):
         rio.read_positions_ts(tmp_path / "missing")
     with pytest.raises(ValueError, match="unsupported format"):
-        rio.read_trajectory(good, 1.0, file_format="outcar")
+        rio.read_trajectory(good, 1.0, file_format="vasprun.xml")
+    with pytest.raises(ValueError, match="timestep is required"):
+        rio.read_trajectory(good)
+
+
+def _outcar_fixture(tmp_path):
+    import gzip
+    import shutil
+
+    path = tmp_path / "OUTCAR_trajectory"
+    with gzip.open(os.path.join(GOLDEN, "llzo_outcar_trajectory.txt.gz"), "rb") as fin, open(path, "wb") as fout:
+        shutil.copyfileobj(fin, fout)
+    return path
+
+
+def test_outcar_reference_fixture_bit_identical(tmp_path):
+    """``test/tests/test_outcar.py:76-94`` (15 kept frames, last position) and, beyond that pin, the
+    whole array the reference reader returns for its fixture (machine-learned + ab-initio steps)."""
+    path = _outcar_fixture(tmp_path)
+    with np.load(os.path.join(GOLDEN, "llzo_outcar_trajectory.npz")) as data:
+        want, timestep = data["positions_ts"], float(data["timestep"])
+    for threads in (1, 4, 0):
+        trajectory = rio.read_trajectory(path, file_format="outcar", num_threads=threads)
+        assert len(trajectory) == 15 and trajectory.timestep == timestep == 1.0
+        assert np.array_equal(trajectory.positions_ts, want)
+    assert np.allclose(trajectory[-1][-1], np.array([0.83330583, 0.83331287, 0.29209206]))
+    cart, lattice, _ = rio.read_outcar_positions_ts(path, cartesian=True)
+    frac, _, _ = rio.read_outcar_positions_ts(path)
+    assert np.allclose(cart @ np.linalg.inv(lattice), frac, rtol=0, atol=1e-15)
+    assert rio.read_trajectory(path, 2.5, file_format="outcar").timestep == 2.5
+
+
+def _write_outcar(path, lattice, cart_ts, ml_pattern=None, timestep=2.0):
+    """A minimal OUTCAR with the markers the reference reader walks through (outcar.py:46-86,
+    212-241, 481-538)."""
+    frames, atoms, _ = cart_ts.shape
+    with open(path, "w", encoding="utf-8") as fh:
+        fh.write(" vasp.6.4.2 synthetic\n")
+        fh.write(" POTCAR:    PAW_PBE Ti_pv 07Sep2000\n POTCAR:    PAW_PBE O 08Apr2002\n")
+        fh.write(" POTCAR:    PAW_PBE Ti_pv 07Sep2000\n   VRHFIN =Ti: 3p4s3d\n   LEXCH  = PE\n")
+        fh.write(" POTCAR:    PAW_PBE O 08Apr2002\n   VRHFIN =O: s2p4\n")
+        fh.write(f"   ions per type =              {atoms - atoms // 3}  {atoms // 3}\n")
+        fh.write(f"   POTIM  = {timestep:.4f}    time-step for ionic-motion\n")
+        fh.write("      direct lattice vectors                 reciprocal lattice vectors\n")
+        for row in np.eye(3):  # symmetry-reduced cell written before the flags: must be skipped
+            fh.write("  " + "  ".join(f"{x:.9f}" for x in row) + "  0 0 0\n")
+        fh.write(" Write flags\n")
+        fh.write("      direct lattice vectors                 reciprocal lattice vectors\n")
+        for row in lattice:
+            fh.write("  " + "  ".join(f"{x:.9f}" for x in row) + "   0.1 0.2 0.3\n")
+        for s in range(frames):
+            tags = ml_pattern[s] if ml_pattern else [""]
+            for tag in tags:
+                fh.write(f" POSITION                                       TOTAL-FORCE (eV/Angst){tag}\n")
+                fh.write(" -----------------------------------------------------------------------------------\n")
+                for a in range(atoms):
+                    x, y, z = cart_ts[s, a]
+                    fh.write(f"  {x:12.5f} {y:12.5f} {z:12.5f}     0.1 -0.2 0.3\n")
+                fh.write(" -----------------------------------------------------------------------------------\n")
+                fh.write("    total drift:   0.0 0.0 0.0\n")
+
+
+def test_outcar_synthetic_triclinic_and_ml_steps(tmp_path):
+    rng = np.random.default_rng(12)
+    lattice = np.array([[9.0, 0.3, -0.2], [1.1, 8.0, 0.4], [-0.7, 0.9, 10.0]])
+    cart = rng.uniform(-3, 12, size=(40, 12, 3))
+    # per stored step: an ML block alone, an ML block followed by its ab-initio repeat (dropped),
+    # or a plain ab-initio block
+    pattern = [[" (ML)"], [" (ML)", ""], [""]]
+    ml_pattern = [pattern[s % 3] for s in range(40)]
+    path = tmp_path / "OUTCAR"
+    _write_outcar(path, lattice, cart, ml_pattern)
+    written = np.array([[[float(f"{x:12.5f}") for x in atom] for atom in frame] for frame in cart])
+    got_cart, got_lattice, timestep = rio.read_outcar_positions_ts(path, cartesian=True)
+    assert timestep == 2.0 and np.array_equal(got_lattice, np.round(lattice, 9))
+    assert np.array_equal(got_cart, written)
+    want = np.array([frame @ np.linalg.inv(got_lattice) for frame in written])  # outcar.py:529
+    got, _, _ = rio.read_outcar_positions_ts(path, num_threads=3)
+    assert np.allclose(got, want, rtol=0, atol=4e-16)
+    trajectory = rio.read_trajectory(path, file_format="outcar")
+    assert np.allclose(trajectory.positions_ts, want - want // 1, rtol=0, atol=4e-16)
+
+
+def test_outcar_malformed(tmp_path):
+    lattice = np.eye(3) * 5
+    cart = np.random.default_rng(1).uniform(0, 5, size=(3, 6, 3))
+    good = tmp_path / "good"
+    _write_outcar(good, lattice, cart)
+    text = open(good, encoding="utf-8").read()
+    assert rio.read_outcar_positions_ts(good)[0].shape == (3, 6, 3)
+    (tmp_path / "nopotcar").write_text(text.replace("POTCAR:    ", "POTCAR: "))
+    with pytest.raises(rio.InvalidFileException, match="POTCAR block not found"):
+        rio.read_trajectory(tmp_path / "nopotcar", file_format="outcar")
+    (tmp_path / "badsym").write_text(text.replace("PAW_PBE O 08Apr2002", "PAW_PBE Qq 08Apr2002", 1))
+    with pytest.raises(rio.InvalidFileException, match="POTCAR block could not be parsed"):
+        rio.read_trajectory(tmp_path / "badsym", file_format="outcar")
+    (tmp_path / "notime").write_text(text.replace("time-step for ionic-motion", "time step"))
+    with pytest.raises(rio.InvalidFileException, match="timestep not found"):
+        rio.read_trajectory(tmp_path / "notime", file_format="outcar")
+    (tmp_path / "noflags").write_text(text.replace("Write flags", "flags"))
+    with pytest.raises(rio.InvalidFileException, match="outcar does not have expected format"):
+        rio.read_trajectory(tmp_path / "noflags", file_format="outcar")
+    (tmp_path / "nomd").write_text(text.replace("TOTAL-FORCE", "TOTAL FORCE"))
+    with pytest.raises(rio.InvalidFileException, match="no trajectory found"):
+        rio.read_trajectory(tmp_path / "nomd", file_format="outcar")
+    lines = text.splitlines()
+    (tmp_path / "short").write_text("\n".join(lines[:-5]) + "\n")
+    with pytest.raises(rio.InvalidFileException, match="Cartesian positions could not be parsed"):
+        rio.read_trajectory(tmp_path / "short", file_format="outcar")
 
 
 @pytest.mark.gpu

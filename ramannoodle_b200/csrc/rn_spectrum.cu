@@ -304,7 +304,7 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
 }
 
 template <int SGN, int LOAD, int STORE, int LOG2TILE>
-__global__ void __launch_bounds__((1 << LOG2TILE) / 8, LOG2TILE == kLog2TileSmall ? (STORE == STORE_MULH ? 4 : 6) : (STORE == STORE_MULH ? 2 : 3))
+__global__ void __launch_bounds__((1 << LOG2TILE) / 8, LOG2TILE == kLog2TileSmall ? (STORE == STORE_MULH ? 5 : 7) : (STORE == STORE_MULH ? 2 : 3))
     fft_tile_kernel(PassParams P) {
     extern __shared__ __align__(16) unsigned char fft_smem[];
     double2* S = reinterpret_cast<double2*>(fft_smem);

@@ -33,6 +33,7 @@ constexpr int kAmpStride = 65;  // doubles per frame row of the amplitude tile
 // A/B hook (rn_debug_set_dense_config): generation 1 = rn_polarizability.cu, 3 = warp-specialised with
 // the piecewise-polynomial epilogue, 4 = warp-specialised with the chained-DMMA epilogue (default)
 static int g_dense_version = 4;
+static int g_dense_split = 1;  // 0 = never, 1 = when whole tiles would leave SMs idle, 2 = always (tests)
 
 // ------------------------------------------------------------------------------------
 // Third generation: warp-specialised.  Warps 0-3 only issue LDS + DMMA (one MMA warp per
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(384, 1)
     dense_kernel_tp(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ V,
                     const double* __restrict__ tp_x0, const double* __restrict__ tp_brk,
                     const double* __restrict__ tp_c8, const double* __restrict__ tp_c9, int64_t num_frames, int K, int Kv, int Jpad, int accumulate,
-                    Alpha0 a0, double* __restrict__ alpha, AlphaPeers peers) {
+                    int split, Alpha0 a0, double* __restrict__ alpha, AlphaPeers peers) {
     constexpr int FT = 128;    // frames per tile: 8 MMA warps x 16
     constexpr int MMAW = 8;    // MMA warps (two per scheduler: one covers the other's LDS / barrier bubbles)
     constexpr int MTW = 2;     // 8-frame groups per MMA warp
@@ -298,8 +299,21 @@ __global__ void __launch_bounds__(384, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunks = Kv / kKC2;
     const int jtiles = Jpad / kJT2;
-    const int64_t total = (int64_t)jtiles * chunks;
     const int64_t num_tiles = (num_frames + FT - 1) / FT;
+    // Work units are (frame tile, DOF tile) pairs; CTA b owns the contiguous range [u0, u1).  Normally
+    // the ranges are whole frame tiles.  With `split` (few frame tiles per SM: short trajectories)
+    // they are balanced to the unit, a frame tile shared by two CTAs is finished with atomic adds
+    // into rows the caller pre-filled, and no SM idles through a partial last wave.
+    int64_t u0, u1;
+    if (split) {
+        const int64_t units = num_tiles * jtiles;
+        u0 = units * blockIdx.x / gridDim.x;
+        u1 = units * (blockIdx.x + 1) / gridDim.x;
+    } else {
+        u0 = (num_tiles * blockIdx.x / gridDim.x) * jtiles;
+        u1 = (num_tiles * (blockIdx.x + 1) / gridDim.x) * jtiles;
+    }
+    const int64_t tile_begin = u0 / jtiles, tile_end = (u1 + jtiles - 1) / jtiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages2; s++) {
@@ -327,17 +341,20 @@ __global__ void __launch_bounds__(384, 1)
 
         uint32_t issued = 0;   // chunks issued so far (running over all tiles: ring stage / parity)
         uint32_t wrapped = 0;  // chunks handed to the MMA warps so far
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int64_t tile = tile_begin; tile < tile_end; tile++) {
             const int64_t frame0 = tile * FT;
+            const int jt_lo = (int)(max(u0, tile * jtiles) - tile * jtiles);
+            const int jt_hi = (int)(min(u1, (tile + 1) * jtiles) - tile * jtiles);
+            const int64_t total = (int64_t)(jt_hi - jt_lo) * chunks;
             const double* a_src_row[A_ITEMS];
 #pragma unroll
             for (int r = 0; r < A_ITEMS; r++) {
                 const int64_t frame = frame0 + a_row0 + r * A_ROWSTEP;
                 a_src_row[r] = (frame < num_frames) ? in + frame * (int64_t)K + a_seg * A_ELEMS : nullptr;
             }
-            int is_kc = 0, is_jt = 0;
+            int is_kc = 0, is_jt = jt_lo;
             auto issue = [&]() {
-                if (is_jt < jtiles) {
+                if (is_jt < jt_hi) {
                     const uint32_t st = issued & (kStages2 - 1);
                     if (issued >= (uint32_t)kStages2) mbar_wait2(empty0 + 8 * st, ((issued >> 2) - 1) & 1);
                     const int col = is_kc * kKC2 + a_seg * A_ELEMS;
@@ -405,13 +422,17 @@ __global__ void __launch_bounds__(384, 1)
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp;  // frames 16*wm .. 16*wm+15
     uint32_t consumed = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int64_t tile = tile_begin; tile < tile_end; tile++) {
         const int64_t frame0 = tile * FT;
+        const int jt_lo = (int)(max(u0, tile * jtiles) - tile * jtiles);
+        const int jt_hi = (int)(min(u1, (tile + 1) * jtiles) - tile * jtiles);
+        const int64_t total = (int64_t)(jt_hi - jt_lo) * chunks;
+        const bool shared_tile = (jt_lo != 0) || (jt_hi != jtiles);  // other CTAs add to the same rows
         double out[MTW][2], o9[MTW];
 #pragma unroll
         for (int mt = 0; mt < MTW; mt++) out[mt][0] = out[mt][1] = o9[mt] = 0.0;
         double acc[MTW][8][2];
-        int kc = 0, jt = 0;
+        int kc = 0, jt = jt_lo;
         for (int64_t c = 0; c < total; c++) {
             if (kc == 0) {
 #pragma unroll
@@ -516,7 +537,15 @@ __global__ void __launch_bounds__(384, 1)
             v9 += __shfl_xor_sync(0xffffffffu, v9, 1);
             v9 += __shfl_xor_sync(0xffffffffu, v9, 2);
             const int64_t frame = frame0 + wm * 8 * MTW + mt * 8 + g;
-            if (frame < num_frames) {
+            if (frame < num_frames && shared_tile) {
+                // split schedule: the rows were pre-filled by the caller; the CTA holding DOF tile 0 adds
+                // the constant on top of its partial sum
+                double* dst = alpha + frame * 9;
+                const bool first = (jt_lo == 0);
+                atomicAdd(dst + 2 * t, out[mt][0] + (first ? a0.v[2 * t] : 0.0));
+                atomicAdd(dst + 2 * t + 1, out[mt][1] + (first ? a0.v[2 * t + 1] : 0.0));
+                if (t == 0) atomicAdd(dst + 8, v9 + (first ? a0.v[8] : 0.0));
+            } else if (frame < num_frames) {
                 double* dst = alpha + frame * 9;
                 // a0 holds what must be added on top of the running value (see launch_tp_cfg)
                 const double b0 = (accumulate ? dst[2 * t] : 0.0) + a0.v[2 * t];
@@ -543,14 +572,31 @@ static int launch_tp_cfg(const rn_model* m, const double* d_in, bool wrap, bool 
                          double* d_alpha, cudaStream_t stream, const AlphaPeers& peers) {
     // constants: alpha0_tp = alpha0 + sum of the dense DOFs' constant terms.  When the affine kernel
     // already wrote alpha0 + D.G (accumulate), only the dense constants remain to be added.
-    Alpha0 a0;
-    for (int q = 0; q < 9; q++) a0.v[q] = accumulate ? (m->alpha0_tp[q] - m->alpha0[q]) : m->alpha0_tp[q];
     const int K = (int)m->dim;
     constexpr int FT = 128;
     const bool align16 = (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (K % 2 == 0);
     const size_t smem = ((size_t)kStages2 * (FT + kJT2) * kRS2) * sizeof(double) + 128;
     const int64_t tiles = (num_frames + FT - 1) / FT;
-    const int grid = (int)std::min<int64_t>(tiles, m->sm_count);
+    int grid = (int)std::min<int64_t>(tiles, m->sm_count);
+    // Whole frame tiles per CTA leave SMs idle in the last wave when there are few tiles per SM
+    // (100k STO frames: 782 tiles on 148 SMs = 5.3 -> 6 rounds; 10k frames: 79 tiles, 69 SMs idle).
+    // Then the (frame tile, DOF tile) units are balanced over all SMs instead; shared tiles finish
+    // with atomic adds, so the rows are pre-filled (alpha0) and the kernel runs in accumulate mode.
+    // Not used with fused peer stores (the peers need finished rows).
+    const int64_t jtiles = m->dense_pad / kJT2;
+    const int64_t rounds = (tiles + m->sm_count - 1) / m->sm_count;
+    const bool split = g_dense_split != 0 && peers.count == 0 && tiles * jtiles >= 2 &&
+                       (g_dense_split == 2 || (double)(rounds * m->sm_count) > 1.04 * (double)tiles);
+    if (split) {
+        grid = (int)std::min<int64_t>(tiles * jtiles, m->sm_count);
+        if (!accumulate) {
+            int rc = launch_fill_alpha0(m, num_frames, d_alpha, stream);
+            if (rc != RN_OK) return rc;
+            accumulate = true;
+        }
+    }
+    Alpha0 a0;
+    for (int q = 0; q < 9; q++) a0.v[q] = accumulate ? (m->alpha0_tp[q] - m->alpha0[q]) : m->alpha0_tp[q];
     const double* V = wrap ? m->d_v_frac : m->d_v_cart;
 #define RN_TP_LAUNCH(W, A)                                                                                   \
     {                                                                                                        \
@@ -558,7 +604,7 @@ static int launch_tp_cfg(const rn_model* m, const double* d_in, bool wrap, bool 
         RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
         kern<<<grid, 384, smem, stream>>>(d_in, m->d_ref_wrapped, V, m->d_tp_x0, m->d_tp_brk, m->d_tp_c8,   \
                                           m->d_tp_c9, num_frames, K, (int)m->v_cols, (int)m->dense_pad,      \
-                                          accumulate ? 1 : 0, a0, d_alpha, peers);                           \
+                                          accumulate ? 1 : 0, split ? 1 : 0, a0, d_alpha, peers);            \
     }
     if (wrap) {
         if (align16) RN_TP_LAUNCH(true, true) else RN_TP_LAUNCH(true, false)
@@ -667,3 +713,5 @@ extern "C" void rn_debug_set_dense_config(int version, int unused) {
     (void)unused;
     rn::g_dense_version = version;
 }
+// 0 = whole frame tiles per CTA, 1 = automatic (default), 2 = always balance (frame tile, DOF tile) units
+extern "C" void rn_debug_set_dense_split(int mode) { rn::g_dense_split = mode; }

@@ -3,6 +3,8 @@ the golden vectors generated from the unmodified reference.  Tolerance: max|new-
 max|ref| <= 1e-10 (BASELINE.json north_star)."""
 import copy
 
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -70,6 +72,28 @@ def test_against_oracle_ragged_sizes(structure, kind, frames):
     positions = synthetic.make_trajectory(structure, frames, seed=frames, lattice_hops=(frames % 2 == 1))
     want = ora.calc_polarizabilities(oracle_model(state), positions)
     _check(rb.InterpolationModel(state), positions, want)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("structure,kind,frames", [("STO", "cubic", 1000), ("TiO2", "mixed", 2500),
+                                                    ("LLZO", "quadratic", 19_100), ("STO", "cubic", 127)])
+def test_dense_schedules_agree(structure, kind, frames, mode):
+    """The dense kernel's three schedules — whole frame tiles per CTA (0), automatic (1), always
+    balanced (frame tile, DOF tile) units with atomically finished shared tiles (2) — against the
+    oracle, for a pure spline model and for one whose linear DOFs ran through the affine kernel."""
+    hook = _lib.lib().rn_debug_set_dense_split
+    hook.argtypes = [ctypes.c_int]
+    hook.restype = None
+    state = synthetic.make_model(structure, kind, masked_fraction=0.05, seed=3)
+    positions = synthetic.make_trajectory(structure, frames, seed=frames)
+    sel = np.r_[0:min(frames, 300), max(0, frames - 300):frames]
+    want = ora.calc_polarizabilities(oracle_model(state), positions[sel])
+    hook(mode)
+    try:
+        got = rb.InterpolationModel(state).calc_polarizabilities(to_cuda(positions)).cpu().numpy()
+    finally:
+        hook(1)
+    assert rel_err(got[sel], want) <= ALPHA_RTOL
 
 
 def test_affine_kernels_agree_and_force_dense():

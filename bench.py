@@ -250,6 +250,7 @@ def run_b200(args):
     # falls back to one NCCL all-gather), and measure() is spread over the ranks.
     sharded = ShardedTrajectory(trajectory._positions_ts, 1.0, total_frames) if world > 1 else None  # pylint: disable=protected-access
     fused_gather = None
+    split_transforms = None
 
     def step():
         if world > 1:
@@ -309,6 +310,7 @@ def run_b200(args):
     if world > 1:
         from ramannoodle_b200 import distributed as rdist
         fused_gather = bool(rdist._SYMMETRIC_SERIES)  # pylint: disable=protected-access
+        split_transforms = bool(rdist._SYMMETRIC_HALVES)  # pylint: disable=protected-access
 
     hbm_peak, hbm_src = measured_peaks()
     if info["dense_dofs"] == 0:
@@ -374,7 +376,8 @@ def run_b200(args):
                        "atoms": num_atoms, "dofs": state.num_dofs, "path": info,
                        "l2": "inputs larger than L2 (no flush needed)" if frames * num_atoms * 24 > 2 * 126e6
                              else "inputs smaller than L2: cache-resident between steps",
-                       "stages": stage, "fused_allgather": fused_gather},
+                       "stages": stage, "fused_allgather": fused_gather,
+                       "split_transforms": split_transforms},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches),
         }

@@ -130,6 +130,7 @@ int rn_calc_polarizabilities_host_sweep(const rn_model* const* models, int num_m
  * structure/utils.py:27: p - p // 1).  Elementwise, in place allowed (d_out == d_in). */
 int rn_apply_pbc(const double* d_in, double* d_out, int64_t count, void* stream);
 
+
 /* ------------------------------------------------------------------------------------
  * MD Raman spectrum — replaces MDRamanSpectrum.measure (spectrum/_raman.py:241-309) with
  * calc_signal_spectrum (spectrum/utils.py:95-124) evaluated through the identity
@@ -158,6 +159,22 @@ int rn_md_spectrum_finish(int64_t num_frames, const double* d_partial_sum, doubl
                           int laser_correction, double laser_wavelength_nm,
                           int bose_einstein_correction, double temperature_K, double* d_wavenumbers,
                           double* d_intensities, void* stream);
+
+/* A packed transform split over TWO ranks (multi-GPU measure with 2 or >= 6 ranks): the chirp-z
+ * input is zero beyond M <= L/2, so the length-L transform separates by output residue r = k mod 2
+ * into two length-L/2 transforms.  rn_md_spectrum_half runs residue `residue` (0/1) of part `part`
+ * and writes its length-L/2 inverse transform (rn_spectrum_half_length(plan) complex doubles) to
+ * d_z_out — memory the partner rank can read (symmetric memory over NVLink); skip_energy != 0
+ * reuses the series energies a previous call on the same plan and series computed.
+ * rn_md_spectrum_half_combine then finishes the half of the bins this residue owns from both
+ * residues' buffers (d_z_res0 / d_z_res1: one local, one the partner's) into d_partial (P doubles;
+ * other bins zeroed unless accumulate != 0).  Summed over parts and residues (all-reduce) the partials
+ * equal those of rn_md_spectrum_part; rn_md_spectrum_finish completes the spectrum. */
+int64_t rn_spectrum_half_length(const rn_spectrum_plan* plan);
+int rn_md_spectrum_half(rn_spectrum_plan* plan, const double* d_alpha, int part, int residue,
+                        double* d_z_out, int skip_energy, void* stream);
+int rn_md_spectrum_half_combine(rn_spectrum_plan* plan, int part, int residue, const double* d_z_res0,
+                                const double* d_z_res1, double* d_partial, int accumulate, void* stream);
 /* calc_signal_spectrum(signal, sampling_rate) (spectrum/utils.py:95-124) for one real signal of
  * length M = S-1 of the plan: outputs ceil(M/2) points (bin 0 included). */
 int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal, double sampling_rate,

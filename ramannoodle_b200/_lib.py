@@ -49,6 +49,11 @@ PROTOTYPES = {
                                       ctypes.c_void_p, ctypes.c_void_p]),
     "rn_md_spectrum_part": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_void_p]),
+    "rn_spectrum_half_length": (ctypes.c_int64, [ctypes.c_void_p]),
+    "rn_md_spectrum_half": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "rn_md_spectrum_half_combine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "rn_md_spectrum_finish": (ctypes.c_int, [ctypes.c_int64, ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
                                              ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]),

@@ -36,6 +36,11 @@ struct rn_spectrum_plan {
     double* d_partial = nullptr;  // energy_blocks * 8
     double* d_energy = nullptr;   // 8
     int energy_blocks = 0;
+    // half-length machinery for transforms split over two ranks (rn_md_spectrum_half): a plan of
+    // length L/2 that shares the chirp table, and the filter spectrum decimated by residue
+    rn_spectrum_plan* half = nullptr;
+    double2* d_hhalf[2] = {nullptr, nullptr};  // H[r + 2k'], k' < L/2
+    bool owns_chirp = true;
 };
 
 namespace rn {
@@ -99,6 +104,28 @@ __device__ __forceinline__ void dft8(double2* v) {
     v[7] = csub(e[3], o3);
 }
 
+// np.diff of the series (_raman.py:282) packed two real signals per complex sequence: (c1, c2) >= 0
+// are tensor components; c1 == -1: (xx - yy, yy - zz), the anisotropy differences (_raman.py:289-291);
+// c1 == -2: (trace, xy) (_raman.py:286-288,292)
+__device__ __forceinline__ void alpha_signal(const double* __restrict__ src, int64_t n, int c1, int c2, double& d1,
+                                             double& d2) {
+    const double* a = src + n * 9;
+    if (c1 >= 0) {
+        d1 = __ldg(a + 9 + c1) - __ldg(a + c1);
+        d2 = __ldg(a + 9 + c2) - __ldg(a + c2);
+    } else {
+        const double xx = __ldg(a + 9) - __ldg(a), yy = __ldg(a + 13) - __ldg(a + 4);
+        const double zz = __ldg(a + 17) - __ldg(a + 8);
+        if (c1 == -1) {
+            d1 = xx - yy;
+            d2 = yy - zz;
+        } else {
+            d1 = xx + yy + zz;
+            d2 = __ldg(a + 10) - __ldg(a + 1);
+        }
+    }
+}
+
 // ---- tiled Stockham FFT ---------------------------------------------------------------------
 // A length-L (power of two) transform is 1-4 global passes.  Pass i is a radix-R_i Stockham step
 // (R_i <= 256): out[(j-k) R + k + y Ns] = DFT_R( in[j + x L/R] * W_{Ns R}^{k x} )[y], k = j mod Ns.
@@ -111,7 +138,7 @@ __device__ __forceinline__ void dft8(double2* v) {
 // host-computed) tables: a two-level table for W_L and a 4096-entry table for the sub-pass
 // twiddles.  The Bluestein pre-multiply (load), the filter multiply (store of the forward
 // transform) and the chirp post-multiply (store of the inverse transform) are fused in.
-enum { LOAD_PLAIN = 0, LOAD_ALPHA = 1, LOAD_SIGNAL = 2 };
+enum { LOAD_PLAIN = 0, LOAD_ALPHA = 1, LOAD_SIGNAL = 2, LOAD_ALPHA_TW = 3 };  // _TW: times W_{2L}^n (split transforms)
 enum { STORE_PLAIN = 0, STORE_POST = 1, STORE_MULH = 2 };
 
 constexpr int kMaxLog2R = 8;  // sub-transforms of at most 256 points per pass
@@ -138,6 +165,9 @@ struct PassParams {
     int64_t M;
     const double2* chirp;  // LOAD_ALPHA / LOAD_SIGNAL / STORE_POST
     double2* spec;         // STORE_POST
+    const double2* rwhi;   // LOAD_ALPHA_TW: two-level table of the double-length transform
+    const double2* rwlo;
+    int rsplit;
 };
 
 template <int SGN, int LOAD, int STORE, int RAD>
@@ -158,28 +188,15 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
         double2 v = make_double2(0.0, 0.0);
         if (n < P.M) {
             double d1, d2 = 0.0;
-            if (LOAD == LOAD_ALPHA) {
-                // np.diff of the series (_raman.py:282), two real signals per complex sequence
-                const double* a = P.src + n * 9;
-                if (P.c1 >= 0) {  // two tensor components
-                    d1 = __ldg(a + 9 + P.c1) - __ldg(a + P.c1);
-                    d2 = __ldg(a + 9 + P.c2) - __ldg(a + P.c2);
-                } else {
-                    const double xx = __ldg(a + 9) - __ldg(a), yy = __ldg(a + 13) - __ldg(a + 4);
-                    const double zz = __ldg(a + 17) - __ldg(a + 8);
-                    if (P.c1 == -1) {  // (xx - yy, yy - zz): the anisotropy differences (_raman.py:289-291)
-                        d1 = xx - yy;
-                        d2 = yy - zz;
-                    } else {  // (trace, xy) (_raman.py:286-288,292)
-                        d1 = xx + yy + zz;
-                        d2 = __ldg(a + 10) - __ldg(a + 1);
-                    }
-                }
+            if (LOAD == LOAD_ALPHA || LOAD == LOAD_ALPHA_TW) {
+                alpha_signal(P.src, n, P.c1, P.c2, d1, d2);
             } else {
                 d1 = __ldg(P.src + n);
             }
             const double2 c = __ldg(P.chirp + n);
             v = make_double2(d1 * c.x - d2 * c.y, d1 * c.y + d2 * c.x);
+            if (LOAD == LOAD_ALPHA_TW)  // residue-1 input of a split transform: a[n] W_{2L}^n
+                v = cmul(v, cmul(__ldg(P.rwhi + (n >> P.rsplit)), __ldg(P.rwlo + (n & (((int64_t)1 << P.rsplit) - 1)))));
         }
         return v;
     };
@@ -321,6 +338,9 @@ struct FftIo {
     const double* src = nullptr;
     int c1 = 0, c2 = 0;
     double2* spec = nullptr;
+    const double2* rwhi = nullptr;
+    const double2* rwlo = nullptr;
+    int rsplit = 0;
 };
 
 template <int SGN, int LOAD, int STORE, int LOG2TILE>
@@ -380,6 +400,9 @@ static int fft_run(const rn_spectrum_plan* p, const double2* first, double2* las
         P.M = p->M;
         P.chirp = p->d_chirp;
         P.spec = io.spec;
+        P.rwhi = io.rwhi;
+        P.rwlo = io.rwlo;
+        P.rsplit = io.rsplit;
         const int load = is_first ? io.load : LOAD_PLAIN;
         const int store = is_last ? io.store : STORE_PLAIN;
         int rc = RN_ERR_UNSUPPORTED;
@@ -392,6 +415,8 @@ static int fft_run(const rn_spectrum_plan* p, const double2* first, double2* las
         RN_PASS(LOAD_ALPHA, STORE_MULH)
         RN_PASS(LOAD_SIGNAL, STORE_PLAIN)
         RN_PASS(LOAD_SIGNAL, STORE_MULH)
+        RN_PASS(LOAD_ALPHA_TW, STORE_PLAIN)
+        RN_PASS(LOAD_ALPHA_TW, STORE_MULH)
 #undef RN_PASS
         if (rc != RN_OK) {
             if (rc == RN_ERR_UNSUPPORTED) set_error("unsupported FFT pass configuration");
@@ -634,11 +659,14 @@ static int bluestein_transform(rn_spectrum_plan* p, const FftIo& in_io, double2*
 
 static void destroy_plan(rn_spectrum_plan* p) {
     if (!p) return;
+    destroy_plan(p->half);
+    cudaFree(p->d_hhalf[0]);
+    cudaFree(p->d_hhalf[1]);
     cudaFree(p->d_buf0);
     cudaFree(p->d_buf1);
     cudaFree(p->d_filter);
     cudaFree(p->d_spec);
-    cudaFree(p->d_chirp);
+    if (p->owns_chirp) cudaFree(p->d_chirp);
     cudaFree(p->d_whi);
     cudaFree(p->d_wlo);
     cudaFree(p->d_wsub);
@@ -652,6 +680,157 @@ static double2 unit_root(int64_t num, int64_t den) {
     const long double two_pi = 6.283185307179586476925286766559005768L;
     const long double ang = two_pi * (long double)num / (long double)den;
     return make_double2((double)cosl(ang), (double)-sinl(ang));
+}
+
+// pass structure + twiddle tables + work buffers of a length-2^log2l transform
+static int setup_fft_core(rn_spectrum_plan* p, int log2l) {
+    const int64_t L = (int64_t)1 << log2l;
+    p->L = L;
+    p->log2l = log2l;
+    // sub-transforms of at most 256 points (>= 64-byte global chunks), as even as possible
+    p->num_passes = (log2l + kMaxLog2R - 1) / kMaxLog2R;
+    int large_min = kLargeTileMinLog2L;
+    if (const char* env = getenv("RN_FFT_LARGE_TILE_MIN_LOG2L")) large_min = atoi(env);  // tuning hook
+    p->log2tile = (log2l >= large_min) ? kLog2TileLarge : kLog2TileSmall;
+    for (int i = 0, rem = log2l; i < p->num_passes; i++) {
+        const int left = p->num_passes - i;
+        p->pass_log2r[i] = (rem + left - 1) / left;
+        rem -= p->pass_log2r[i];
+    }
+    p->split = log2l / 2;
+    const int64_t n_hi = L >> p->split, n_lo = (int64_t)1 << p->split;
+    cudaError_t err = cudaSuccess;
+    auto alloc = [&](void** ptr, size_t bytes) {
+        if (err == cudaSuccess) err = cudaMalloc(ptr, bytes);
+    };
+    alloc((void**)&p->d_buf0, sizeof(double2) * L);
+    alloc((void**)&p->d_buf1, sizeof(double2) * L);
+    alloc((void**)&p->d_whi, sizeof(double2) * n_hi);
+    alloc((void**)&p->d_wlo, sizeof(double2) * n_lo);
+    alloc((void**)&p->d_wsub, sizeof(double2) * 4096);
+    if (err != cudaSuccess) {
+        set_error("cudaMalloc failed while creating a length-2^%d transform: %s", log2l, cudaGetErrorString(err));
+        cudaGetLastError();
+        return RN_ERR_OUT_OF_MEMORY;
+    }
+    std::vector<double2> whi((size_t)n_hi), wlo((size_t)n_lo), wsub((size_t)4096);
+    for (int64_t a = 0; a < n_hi; a++) whi[(size_t)a] = unit_root(a << p->split, L);
+    for (int64_t b = 0; b < n_lo; b++) wlo[(size_t)b] = unit_root(b, L);
+    for (int m = 0; m < 4096; m++) wsub[(size_t)m] = unit_root(m, 4096);
+    cudaError_t e1 = cudaMemcpy(p->d_whi, whi.data(), sizeof(double2) * n_hi, cudaMemcpyHostToDevice);
+    if (e1 == cudaSuccess) e1 = cudaMemcpy(p->d_wlo, wlo.data(), sizeof(double2) * n_lo, cudaMemcpyHostToDevice);
+    if (e1 == cudaSuccess) e1 = cudaMemcpy(p->d_wsub, wsub.data(), sizeof(double2) * 4096, cudaMemcpyHostToDevice);
+    if (e1 != cudaSuccess) {
+        set_error("twiddle table upload failed: %s", cudaGetErrorString(e1));
+        return RN_ERR_CUDA;
+    }
+    return RN_OK;
+}
+
+// ---- transforms split over two ranks --------------------------------------------------------
+// The chirp-z input a[n] = x[n] c[n] is zero for n >= M and L >= 2M-1, so the length-L transform
+// splits by output residue r = k mod 2 into two length-L/2 transforms with no butterfly stage in
+// front:  A[r + 2k'] = FFT_{L/2}( a[n] W_L^{n r} )[k'].  After the filter multiply (H[r + 2k']) and
+// a length-L/2 inverse transform z_r, the chirp-z output is  y[m] = z_0[m] + W_L^{-m} z_1[m]
+// (m < M <= L/2).  Two ranks each run one residue (half the work of a full transform), exchange
+// nothing but reads of the partner's z_r over NVLink, and each finishes half of the bins.
+
+__global__ void __launch_bounds__(256) decimate_filter_kernel(const double2* __restrict__ H, int64_t Lh,
+                                                              double2* __restrict__ h0, double2* __restrict__ h1) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < Lh; k += (int64_t)gridDim.x * blockDim.x) {
+        h0[k] = H[2 * k];
+        h1[k] = H[2 * k + 1];
+    }
+}
+
+// part_combine_kernel on the bins this residue's rank owns (residue 0: the lower half of the bins,
+// residue 1: the upper half), from the two half-length inverse transforms
+__global__ void __launch_bounds__(256) half_combine_kernel(const double2* __restrict__ z0, const double2* __restrict__ z1,
+                                                           const double2* __restrict__ chirp_table,
+                                                           const double2* __restrict__ whi,
+                                                           const double2* __restrict__ wlo, int split,
+                                                           const double* __restrict__ energy, int part, int residue,
+                                                           int64_t M, int64_t L, int64_t points, int accumulate,
+                                                           double* __restrict__ partial) {
+    const double scale = 1.0 / (double)L;
+    const int64_t cut = points / 2;  // bins o < cut belong to residue 0
+    auto spec_at = [&](int64_t m) {
+        double2 w = cmul(__ldg(whi + (m >> split)), __ldg(wlo + (m & (((int64_t)1 << split) - 1))));
+        w.y = -w.y;  // W_L^{-m}
+        const double2 y = cadd(z0[m], cmul(w, z1[m]));
+        double2 v = cmul(y, __ldg(chirp_table + m));
+        v.x *= scale;
+        v.y *= scale;
+        return v;
+    };
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < points; o += (int64_t)gridDim.x * blockDim.x) {
+        const bool mine = residue ? (o >= cut) : (o < cut);
+        double out = 0.0;
+        if (mine) {
+            const int64_t k = o + 1;
+            const double2 zk = spec_at(k), zm = spec_at(M - k);
+            const double2 x1 = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+            const double2 x2 = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+            auto power = [](double2 v, double e) { return (v.x * v.x + v.y * v.y + e) * 0.5; };
+            if (part == 0) {
+                const double2 x3 = make_double2(-(x1.x + x2.x), -(x1.y + x2.y));
+                out = 7.0 * ((1.0 / 2.0) * power(x1, energy[1]) + (1.0 / 2.0) * power(x2, energy[2]) +
+                             (1.0 / 2.0) * power(x3, energy[3]));
+            } else if (part == 1) {
+                out = 45.0 * ((1.0 / 9.0) * power(x1, energy[0])) + 7.0 * (3.0 * power(x2, energy[4]));
+            } else {
+                out = 7.0 * (3.0 * power(x1, energy[5]) + 3.0 * power(x2, energy[6]));
+            }
+        }
+        if (accumulate) {
+            if (mine) partial[o] += out;
+        } else {
+            partial[o] = out;
+        }
+    }
+}
+
+static int ensure_half_plan(rn_spectrum_plan* p) {
+    if (p->half) return RN_OK;
+    if (p->log2l < 4) {
+        set_error("series too short for a split transform");
+        return RN_ERR_UNSUPPORTED;
+    }
+    rn_spectrum_plan* h = new rn_spectrum_plan();
+    h->device = p->device;
+    h->sm_count = p->sm_count;
+    h->S = p->S;
+    h->M = p->M;
+    h->d_chirp = p->d_chirp;
+    h->owns_chirp = false;
+    int rc = setup_fft_core(h, p->log2l - 1);
+    if (rc == RN_OK) {
+        cudaError_t err = cudaMalloc((void**)&p->d_hhalf[0], sizeof(double2) * h->L);
+        if (err == cudaSuccess) err = cudaMalloc((void**)&p->d_hhalf[1], sizeof(double2) * h->L);
+        if (err != cudaSuccess) {
+            set_error("cudaMalloc failed for the decimated filter: %s", cudaGetErrorString(err));
+            cudaGetLastError();
+            rc = RN_ERR_OUT_OF_MEMORY;
+        }
+    }
+    if (rc == RN_OK) {
+        decimate_filter_kernel<<<grid_for(h->L, p->sm_count), 256>>>(p->d_filter, h->L, p->d_hhalf[0], p->d_hhalf[1]);
+        RN_LAUNCHED();
+        cudaError_t e2 = cudaStreamSynchronize(nullptr);
+        if (e2 != cudaSuccess) {
+            set_error("split-transform initialisation failed: %s", cudaGetErrorString(e2));
+            rc = RN_ERR_CUDA;
+        }
+    }
+    if (rc != RN_OK) {
+        destroy_plan(h);
+        cudaFree(p->d_hhalf[0]);
+        cudaFree(p->d_hhalf[1]);
+        p->d_hhalf[0] = p->d_hhalf[1] = nullptr;
+        return rc;
+    }
+    p->half = h;
+    return RN_OK;
 }
 
 }  // namespace rn
@@ -690,33 +869,19 @@ extern "C" int rn_spectrum_plan_create(int64_t num_frames, int device, rn_spectr
         log2l++;
     }
     RN_CHECK_ARG(log2l <= 30, "series too long for one spectrum plan (%lld frames)", (long long)num_frames);
-    p->L = L;
-    p->log2l = log2l;
-    // pass structure: sub-transforms of at most 256 points (>= 64-byte global chunks), as even as possible
-    p->num_passes = (log2l + kMaxLog2R - 1) / kMaxLog2R;
-    int large_min = kLargeTileMinLog2L;
-    if (const char* env = getenv("RN_FFT_LARGE_TILE_MIN_LOG2L")) large_min = atoi(env);  // tuning hook
-    p->log2tile = (log2l >= large_min) ? kLog2TileLarge : kLog2TileSmall;
-    for (int i = 0, rem = log2l; i < p->num_passes; i++) {
-        const int left = p->num_passes - i;
-        p->pass_log2r[i] = (rem + left - 1) / left;
-        rem -= p->pass_log2r[i];
+    int core_rc = setup_fft_core(p, log2l);
+    if (core_rc != RN_OK) {
+        destroy_plan(p);
+        return core_rc;
     }
-    p->split = log2l / 2;
     p->energy_blocks = (int)std::min<int64_t>((p->M + 255) / 256, (int64_t)p->sm_count * 4);
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void** ptr, size_t bytes) {
         if (err == cudaSuccess) err = cudaMalloc(ptr, bytes);
     };
-    const int64_t n_hi = L >> p->split, n_lo = (int64_t)1 << p->split;
-    alloc((void**)&p->d_buf0, sizeof(double2) * L);
-    alloc((void**)&p->d_buf1, sizeof(double2) * L);
     alloc((void**)&p->d_filter, sizeof(double2) * L);
     alloc((void**)&p->d_spec, sizeof(double2) * 3 * p->M);
     alloc((void**)&p->d_chirp, sizeof(double2) * p->M);
-    alloc((void**)&p->d_whi, sizeof(double2) * n_hi);
-    alloc((void**)&p->d_wlo, sizeof(double2) * n_lo);
-    alloc((void**)&p->d_wsub, sizeof(double2) * 4096);
     alloc((void**)&p->d_partial, sizeof(double) * 8 * p->energy_blocks);
     alloc((void**)&p->d_energy, sizeof(double) * 8);
     if (err != cudaSuccess) {
@@ -725,20 +890,6 @@ extern "C" int rn_spectrum_plan_create(int64_t num_frames, int device, rn_spectr
         destroy_plan(p);
         cudaGetLastError();
         return RN_ERR_OUT_OF_MEMORY;
-    }
-    {
-        std::vector<double2> whi((size_t)n_hi), wlo((size_t)n_lo), wsub((size_t)4096);
-        for (int64_t a = 0; a < n_hi; a++) whi[(size_t)a] = unit_root(a << p->split, L);
-        for (int64_t b = 0; b < n_lo; b++) wlo[(size_t)b] = unit_root(b, L);
-        for (int m = 0; m < 4096; m++) wsub[(size_t)m] = unit_root(m, 4096);
-        cudaError_t e1 = cudaMemcpy(p->d_whi, whi.data(), sizeof(double2) * n_hi, cudaMemcpyHostToDevice);
-        if (e1 == cudaSuccess) e1 = cudaMemcpy(p->d_wlo, wlo.data(), sizeof(double2) * n_lo, cudaMemcpyHostToDevice);
-        if (e1 == cudaSuccess) e1 = cudaMemcpy(p->d_wsub, wsub.data(), sizeof(double2) * 4096, cudaMemcpyHostToDevice);
-        if (e1 != cudaSuccess) {
-            set_error("twiddle table upload failed: %s", cudaGetErrorString(e1));
-            destroy_plan(p);
-            return RN_ERR_CUDA;
-        }
     }
     // chirp table, then the filter spectrum H = FFT_L(h) — computed once per plan
     chirp_table_kernel<<<grid_for(p->M, p->sm_count), 256>>>(p->d_chirp, p->M);
@@ -839,6 +990,77 @@ extern "C" int rn_md_spectrum_part(rn_spectrum_plan* plan, const double* d_alpha
     if (rc != RN_OK) return rc;
     part_combine_kernel<<<grid_for(points, plan->sm_count), 256, 0, s>>>(plan->d_spec, plan->d_energy, part, M, L, points,
                                                                         d_partial);
+    RN_LAUNCHED();
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}
+
+// Length (complex elements) of the half transforms: rn_md_spectrum_half writes that many double2.
+extern "C" int64_t rn_spectrum_half_length(const rn_spectrum_plan* plan) { return plan ? plan->L / 2 : 0; }
+
+// One residue (0 or 1) of one packed transform (part 0..2) of measure(): writes the length-L/2
+// inverse transform z_r to d_z_out (device memory other ranks can read, e.g. symmetric memory).
+extern "C" int rn_md_spectrum_half(rn_spectrum_plan* plan, const double* d_alpha, int part, int residue,
+                                   double* d_z_out, int skip_energy, void* stream) {
+    RN_CHECK_ARG(plan != nullptr && d_alpha != nullptr && d_z_out != nullptr, "null pointer");
+    RN_CHECK_ARG(part >= 0 && part <= 2, "part must be 0, 1 or 2");
+    RN_CHECK_ARG(residue == 0 || residue == 1, "residue must be 0 or 1");
+    if (rn_spectrum_num_points(plan->S) == 0) return RN_OK;
+    DeviceGuard guard(plan->device);
+    int rc = ensure_half_plan(plan);
+    if (rc != RN_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rn_spectrum_plan* h = plan->half;
+    if (!skip_energy) {
+        energy_partial_kernel<0><<<plan->energy_blocks, 256, 0, s>>>(d_alpha, plan->M, plan->d_partial);
+        RN_LAUNCHED();
+        energy_final_kernel<<<1, 256, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
+        RN_LAUNCHED();
+    }
+    // forward half transform: the chirp pre-multiply (and, residue 1, the W_L^n twiddle) in the first
+    // pass' load, the decimated filter in the last pass' store
+    double2* fwd = nullptr;
+    FftIo fio;
+    fio.load = residue ? LOAD_ALPHA_TW : LOAD_ALPHA;
+    fio.src = d_alpha;
+    if (part == 0) fio.c1 = -1;
+    else if (part == 1) fio.c1 = -2;
+    else {
+        fio.c1 = 5;  // yz
+        fio.c2 = 2;  // xz
+    }
+    fio.rwhi = plan->d_whi;
+    fio.rwlo = plan->d_wlo;
+    fio.rsplit = plan->split;
+    fio.store = STORE_MULH;
+    fio.H = plan->d_hhalf[residue];
+    rc = fft_run<-1>(h, nullptr, nullptr, fio, s, &fwd);
+    if (rc != RN_OK) return rc;
+    FftIo io;
+    rc = fft_run<+1>(h, fwd, reinterpret_cast<double2*>(d_z_out), io, s);
+    if (rc != RN_OK) return rc;
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}
+
+// Finishes the bins owned by `residue` (0: lower half, 1: upper half) of part `part` from the two
+// residues' inverse transforms (one of them usually the partner rank's, read over NVLink); other bins
+// are set to zero (accumulate == 0) or left alone.  The partial intensities of all parts and both
+// residues add up to what rn_md_spectrum_part produces for the three parts.  Must run after
+// rn_md_spectrum_half on the same plan (series energies).
+extern "C" int rn_md_spectrum_half_combine(rn_spectrum_plan* plan, int part, int residue, const double* d_z_res0,
+                                           const double* d_z_res1, double* d_partial, int accumulate, void* stream) {
+    RN_CHECK_ARG(plan != nullptr, "plan is null");
+    RN_CHECK_ARG(part >= 0 && part <= 2, "part must be 0, 1 or 2");
+    RN_CHECK_ARG(residue == 0 || residue == 1, "residue must be 0 or 1");
+    const int64_t points = rn_spectrum_num_points(plan->S);
+    if (points == 0) return RN_OK;
+    RN_CHECK_ARG(d_z_res0 && d_z_res1 && d_partial, "null pointer");
+    DeviceGuard guard(plan->device);
+    half_combine_kernel<<<grid_for(points, plan->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const double2*>(d_z_res0), reinterpret_cast<const double2*>(d_z_res1), plan->d_chirp,
+        plan->d_whi, plan->d_wlo, plan->split, plan->d_energy, part, residue, plan->M, plan->L, points, accumulate,
+        d_partial);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     return RN_OK;

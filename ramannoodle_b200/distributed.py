@@ -85,6 +85,49 @@ def spectrum_parts(world_size: int, rank: int) -> list[int]:
     return [part for part in range(3) if part % world_size == rank]
 
 
+def spectrum_half_units(world_size: int, rank: int):
+    """Split-transform schedule of ``measure`` (``rn_md_spectrum_half``): each of the three packed
+    transforms is two half-length transforms (output residues 0/1) run by a pair of ranks that read
+    each other's result.  Returns ``(units, partner)`` with ``units`` the ``(part, residue)`` pairs
+    of this rank (slot order) and ``partner`` the rank holding the other residue of every unit, or
+    ``None`` when the world size does not profit (then whole parts are dealt out, ``spectrum_parts``).
+
+    2 ranks: rank r runs residue r of all three parts (3 half transforms each instead of 2 + 1 full
+    ones).  6 or more ranks: ranks 2p and 2p+1 run the residues of part p (one half transform each
+    instead of one full transform on three ranks); further ranks only take part in the barriers."""
+    if not 0 <= rank < world_size:
+        raise ValueError("invalid rank/world_size")
+    if world_size == 2:
+        return [(part, rank) for part in range(3)], 1 - rank
+    if world_size >= 6:
+        if rank < 6:
+            return [(rank // 2, rank % 2)], rank ^ 1
+        return [], None
+    return None
+
+
+_SYMMETRIC_HALVES: dict = {}
+
+
+def symmetric_halves(slots: int, half_length: int, device, group=None):
+    """``(slots, L/2, 2)`` fp64 buffer in symmetric memory for the half-transform results, plus its
+    rendezvous handle (cached: the rendezvous is a collective)."""
+    import torch  # pylint: disable=import-outside-toplevel
+    import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+    import torch.distributed._symmetric_memory as symm_mem  # pylint: disable=import-outside-toplevel
+
+    pg = group if group is not None else dist.group.WORLD
+    key = (int(slots), int(half_length), str(device), pg.group_name)
+    entry = _SYMMETRIC_HALVES.get(key)
+    if entry is None:
+        tensor = symm_mem.empty((int(slots), int(half_length), 2), dtype=torch.float64, device=device)
+        handle = symm_mem.rendezvous(tensor, group=pg.group_name)
+        entry = (tensor, handle)
+        _SYMMETRIC_HALVES.clear()
+        _SYMMETRIC_HALVES[key] = entry
+    return entry
+
+
 class ShardedMDRamanSpectrum(MDRamanSpectrum):
     """``MDRamanSpectrum`` whose ``measure`` is spread over the ranks of a process group.
 
@@ -95,9 +138,42 @@ class ShardedMDRamanSpectrum(MDRamanSpectrum):
     the optional corrections.  With G >= 3 the spectrum stage costs one transform instead of three.
     """
 
-    def __init__(self, polarizability_ts, timestep: float, group=None):
+    def __init__(self, polarizability_ts, timestep: float, group=None, split_transforms: bool = True):
         super().__init__(polarizability_ts, timestep)
         self._group = group
+        # RN_SPLIT_TRANSFORMS=0: A/B switch back to whole transforms per rank
+        self._split_transforms = bool(split_transforms) and os.environ.get("RN_SPLIT_TRANSFORMS", "1") != "0"
+
+    def _measure_split(self, series, plan, total, world, rank, device) -> bool:
+        """Half-transform schedule (``spectrum_half_units``); False if it does not apply here."""
+        import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+
+        schedule = spectrum_half_units(world, rank) if self._split_transforms else None
+        if schedule is None or dist.get_backend(self._group) != "nccl":
+            return False
+        units, partner = schedule
+        half_length = int(_lib.lib().rn_spectrum_half_length(plan.handle))
+        slots = 3 if world == 2 else 1
+        try:
+            zbuf, handle = symmetric_halves(slots, half_length, series.device, self._group)
+        except Exception:  # pylint: disable=broad-except  (no symmetric-memory support on this system)
+            return False
+        stream = _stream(device)
+        handle.barrier()  # the partner is done reading the previous contents
+        for slot, (part, residue) in enumerate(units):
+            status = _lib.lib().rn_md_spectrum_half(plan.handle, ctypes.c_void_p(series.data_ptr()), part, residue,
+                                                    ctypes.c_void_p(zbuf[slot].data_ptr()), 1 if slot > 0 else 0, stream)
+            _lib.check(status, "rn_md_spectrum_half")
+        handle.barrier()  # both residues of every unit are complete
+        for slot, (part, residue) in enumerate(units):
+            own = int(zbuf[slot].data_ptr())
+            other = int(handle.buffer_ptrs[partner]) + slot * half_length * 16
+            res0, res1 = (own, other) if residue == 0 else (other, own)
+            status = _lib.lib().rn_md_spectrum_half_combine(plan.handle, part, residue, ctypes.c_void_p(res0),
+                                                            ctypes.c_void_p(res1), ctypes.c_void_p(total.data_ptr()),
+                                                            1 if slot > 0 else 0, stream)
+            _lib.check(status, "rn_md_spectrum_half_combine")
+        return True
 
     # pylint: disable=too-many-arguments,too-many-positional-arguments,too-many-locals
     def measure_device(self, orientation="polycrystalline", laser_correction=False, laser_wavelength=522,
@@ -132,9 +208,10 @@ class ShardedMDRamanSpectrum(MDRamanSpectrum):
             wavenumbers = torch.empty(points, dtype=torch.float64, device=series.device)
             intensities = torch.empty(points, dtype=torch.float64, device=series.device)
             if points > 0:
-                parts = spectrum_parts(world, rank)
+                plan = _get_plan(num_frames, device)
+                split = world > 1 and self._measure_split(series, plan, total, world, rank, device)
+                parts = [] if split else spectrum_parts(world, rank)
                 if parts:
-                    plan = _get_plan(num_frames, device)
                     partial = torch.empty(points, dtype=torch.float64, device=series.device)
                     for part in parts:
                         status = _lib.lib().rn_md_spectrum_part(plan.handle, ctypes.c_void_p(series.data_ptr()), part,

@@ -13,6 +13,32 @@ import torch.multiprocessing as mp
 from ramannoodle_b200.distributed import shard_bounds
 
 
+def test_spectrum_schedules():
+    """Host-side schedules of the sharded measure: whole parts (``spectrum_parts``) and the two-rank
+    split of every packed transform (``spectrum_half_units``)."""
+    from ramannoodle_b200.distributed import spectrum_half_units, spectrum_parts
+
+    for world in range(1, 9):
+        assert sorted(sum((spectrum_parts(world, r) for r in range(world)), [])) == [0, 1, 2]
+    for world in (2, 6, 7, 8):
+        owned = []
+        for rank in range(world):
+            units, partner = spectrum_half_units(world, rank)
+            owned += units
+            if units:
+                other_units, other_partner = spectrum_half_units(world, partner)
+                assert other_partner == rank and other_units == [(p, 1 - r) for p, r in units]
+            else:
+                assert partner is None and world > 6 and rank >= 6
+        assert sorted(owned) == [(p, r) for p in range(3) for r in range(2)]
+    assert spectrum_half_units(2, 1) == ([(0, 1), (1, 1), (2, 1)], 0)
+    assert spectrum_half_units(8, 5) == ([(2, 1)], 4)
+    for world in (1, 3, 4, 5):
+        assert spectrum_half_units(world, 0) is None
+    with pytest.raises(ValueError):
+        spectrum_half_units(2, 2)
+
+
 def test_shard_bounds_partition_frames():
     for frames in (0, 1, 7, 8, 1000, 1001, 10_000_019):
         for world in (1, 2, 3, 4, 8):

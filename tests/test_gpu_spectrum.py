@@ -211,3 +211,58 @@ def test_sharded_parts_sum_to_measure(frames):
                                      ctypes.c_void_p(wn.data_ptr()), ctypes.c_void_p(inten.data_ptr()), stream) == 0
     assert np.array_equal(wn.cpu().numpy(), ref_wn)
     assert pointwise_rel_err(inten.cpu().numpy(), ref_inten) <= INTENSITY_RTOL
+
+
+@pytest.mark.parametrize("frames", [41, 1000, 4097, 50_001, 300_000])
+def test_split_transforms_sum_to_measure(frames):
+    """The two-rank split of every packed transform (rn_md_spectrum_half + rn_md_spectrum_half_combine:
+    residues 0/1, each finishing half of the bins) emulated on one GPU: the six partial spectra add up
+    to MDRamanSpectrum.measure (oracle, 1e-8) and to rn_md_spectrum_part's (1e-12)."""
+    import ctypes
+
+    from ramannoodle_b200 import _lib
+    from ramannoodle_b200.distributed import spectrum_half_units
+    from ramannoodle_b200.spectrum import _get_plan
+
+    rng = np.random.default_rng(frames + 1)
+    steps = np.arange(frames)[:, None, None]
+    alpha = (6.0 * np.eye(3)[None] + 0.05 * np.sin(0.013 * steps + rng.uniform(0, 6, (1, 3, 3)))
+             + 0.01 * rng.normal(size=(frames, 3, 3)))
+    ref_wn, ref_inten = ora.md_measure(alpha, 1.5, laser_correction=True, laser_wavelength=532)
+    d_alpha = to_cuda(alpha)
+    lib = _lib.lib()
+    plan = _get_plan(frames, 0)
+    points = int(lib.rn_spectrum_num_points(frames))
+    half = int(lib.rn_spectrum_half_length(plan.handle))
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+
+    # schedules: every (part, residue) unit is owned exactly once and partners are mutual
+    for world in (2, 6, 8):
+        owned = []
+        for rank in range(world):
+            units, partner = spectrum_half_units(world, rank)
+            owned += units
+            if units:
+                assert spectrum_half_units(world, partner)[1] == rank
+                assert [(p, 1 - r) for p, r in units] == spectrum_half_units(world, partner)[0]
+        assert sorted(owned) == [(p, r) for p in range(3) for r in range(2)]
+    assert spectrum_half_units(4, 1) is None and spectrum_half_units(1, 0) is None
+
+    total = torch.zeros(points, dtype=torch.float64, device="cuda:0")
+    by_part = torch.zeros(points, dtype=torch.float64, device="cuda:0")
+    for part in range(3):
+        z = torch.full((2, half, 2), float("nan"), dtype=torch.float64, device="cuda:0")
+        for residue in range(2):
+            assert lib.rn_md_spectrum_half(plan.handle, ptr(d_alpha), part, residue, ptr(z[residue]), residue, stream) == 0
+        piece = torch.full((points,), float("nan"), dtype=torch.float64, device="cuda:0")
+        assert lib.rn_md_spectrum_half_combine(plan.handle, part, 0, ptr(z[0]), ptr(z[1]), ptr(piece), 0, stream) == 0
+        assert lib.rn_md_spectrum_half_combine(plan.handle, part, 1, ptr(z[0]), ptr(z[1]), ptr(piece), 1, stream) == 0
+        assert lib.rn_md_spectrum_part(plan.handle, ptr(d_alpha), part, ptr(by_part), stream) == 0
+        assert rel_err(piece.cpu().numpy(), by_part.cpu().numpy()) <= 1e-12
+        total += piece
+    wn = torch.empty_like(total)
+    inten = torch.empty_like(total)
+    assert lib.rn_md_spectrum_finish(frames, ptr(total), 1.5, 1, 532.0, 0, 0.0, ptr(wn), ptr(inten), stream) == 0
+    assert np.array_equal(wn.cpu().numpy(), ref_wn)
+    assert pointwise_rel_err(inten.cpu().numpy(), ref_inten) <= INTENSITY_RTOL

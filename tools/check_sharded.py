@@ -40,7 +40,8 @@ for structure, kind, frames in (("LLZO", "art", 5001), ("STO", "cubic", 1237)):
         ok = ok and good
         from ramannoodle_b200 import distributed as rdist
         used_symm = bool(rdist._SYMMETRIC_SERIES)
-        print(f"rank {rank}/{world} {structure}/{kind} resident={resident} fused={fused} symm={used_symm}: alpha {e_a:.1e} intensity {e_i:.1e} ok={good}",
+        split = bool(rdist._SYMMETRIC_HALVES)
+        print(f"rank {rank}/{world} {structure}/{kind} resident={resident} fused={fused} symm={used_symm} split={split}: alpha {e_a:.1e} intensity {e_i:.1e} ok={good}",
               flush=True)
 flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)

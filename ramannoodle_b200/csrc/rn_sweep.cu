@@ -362,6 +362,21 @@ extern "C" int rn_calc_polarizabilities_sweep(const rn_model* const* models, int
             out.columns = columns;
             double* d_stacked = nullptr;
             const int64_t rows = m->g_rows;
+            {
+                // stream-ordered scratch for the stacked table: keep freed blocks in the device's default
+                // pool across synchronisations (the default threshold of 0 returns them to the driver,
+                // and every chunk of a host sweep would pay a fresh physical allocation)
+                static bool pool_ready[64] = {false};
+                if (m->device < 64 && !pool_ready[m->device]) {
+                    cudaMemPool_t pool = nullptr;
+                    if (cudaDeviceGetDefaultMemPool(&pool, m->device) == cudaSuccess) {
+                        uint64_t keep = 64ull << 20;
+                        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                    }
+                    cudaGetLastError();
+                    pool_ready[m->device] = true;
+                }
+            }
             RN_CUDA(cudaMallocAsync((void**)&d_stacked, sizeof(double) * rows * 8 * nt, s));
             sweep_stack_kernel<<<(unsigned)std::min<int64_t>((rows * 8 * nt + 255) / 256, 1024), 256, 0, s>>>(
                 tabs, rows, columns, 8 * nt, d_stacked);

@@ -688,10 +688,15 @@ static int setup_fft_core(rn_spectrum_plan* p, int log2l) {
     p->L = L;
     p->log2l = log2l;
     // sub-transforms of at most 256 points (>= 64-byte global chunks), as even as possible
-    p->num_passes = (log2l + kMaxLog2R - 1) / kMaxLog2R;
+    // (measured, tools/fft_pass_sweep.sh: two 512-point passes beat three for L = 2^17, 2^18 — 0.110 vs
+    // 0.123 ms at S = 1e5; from 2^19 on the 16/32-byte gathers of larger radices lose)
+    int max_log2r = (log2l == 17 || log2l == 18) ? 9 : kMaxLog2R;
+    if (const char* env = getenv("RN_FFT_MAX_LOG2R")) max_log2r = atoi(env);  // tuning hook
     int large_min = kLargeTileMinLog2L;
     if (const char* env = getenv("RN_FFT_LARGE_TILE_MIN_LOG2L")) large_min = atoi(env);  // tuning hook
     p->log2tile = (log2l >= large_min) ? kLog2TileLarge : kLog2TileSmall;
+    max_log2r = std::max(3, std::min(max_log2r, p->log2tile));
+    p->num_passes = (log2l + max_log2r - 1) / max_log2r;
     for (int i = 0, rem = log2l; i < p->num_passes; i++) {
         const int left = p->num_passes - i;
         p->pass_log2r[i] = (rem + left - 1) / left;

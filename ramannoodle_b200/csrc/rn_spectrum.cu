@@ -178,15 +178,21 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
     const int T = tile >> 3 > 0 ? tile >> 3 : 1;  // active threads (8 elements each)
     const int tid = threadIdx.x;
     const bool active = tid < T;
-    const int64_t cnt = P.L >> P.log2r;  // number of j
-    const int64_t num_tiles = cnt >> P.log2b;
+    // every element index fits in 32 bits (L <= 2^30, checked at plan creation); strides are powers of two
+    typedef uint32_t idx_t;
+    const int log2cnt = 63 - __clzll((unsigned long long)P.L) - P.log2r;  // cnt = L / R = number of j
+    const idx_t num_tiles = (idx_t)1 << (log2cnt - P.log2b);
+    const int log2ns = 63 - __clzll((unsigned long long)P.Ns);
+    const idx_t ns_mask = (idx_t)P.Ns - 1;
+    const idx_t tw_stride = (idx_t)P.tw_stride;
+    const idx_t M32 = (idx_t)P.M;
     constexpr int PER = 8 / RAD;  // first-sub-pass butterflies per thread
     const int nbf = R / RAD;
 
-    auto load = [&](int64_t n) {
+    auto load = [&](idx_t n) {
         if (LOAD == LOAD_PLAIN) return P.in[n];
         double2 v = make_double2(0.0, 0.0);
-        if (n < P.M) {
+        if (n < M32) {
             double d1, d2 = 0.0;
             if (LOAD == LOAD_ALPHA || LOAD == LOAD_ALPHA_TW) {
                 alpha_signal(P.src, n, P.c1, P.c2, d1, d2);
@@ -196,22 +202,22 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
             const double2 c = __ldg(P.chirp + n);
             v = make_double2(d1 * c.x - d2 * c.y, d1 * c.y + d2 * c.x);
             if (LOAD == LOAD_ALPHA_TW)  // residue-1 input of a split transform: a[n] W_{2L}^n
-                v = cmul(v, cmul(__ldg(P.rwhi + (n >> P.rsplit)), __ldg(P.rwlo + (n & (((int64_t)1 << P.rsplit) - 1)))));
+                v = cmul(v, cmul(__ldg(P.rwhi + (n >> P.rsplit)), __ldg(P.rwlo + (n & (((idx_t)1 << P.rsplit) - 1)))));
         }
         return v;
     };
     // gather the 8 elements this thread feeds into the first sub-pass of tile `tl`
-    auto gather = [&](int64_t tl, double2* dst) {
-        const int64_t j_base = tl << P.log2b;
+    auto gather = [&](idx_t tl, double2* dst) {
+        const idx_t j_base = tl << P.log2b;
 #pragma unroll
         for (int t = 0; t < PER; t++) {
             const int u = tid + t * T;
             const int i = u >> P.log2b, b = u & (B - 1);
 #pragma unroll
-            for (int q = 0; q < RAD; q++) dst[t * RAD + q] = load(j_base + b + (int64_t)(i + q * nbf) * cnt);
+            for (int q = 0; q < RAD; q++) dst[t * RAD + q] = load(j_base + b + ((idx_t)(i + q * nbf) << log2cnt));
         }
     };
-    auto out_index = [&](int64_t j_base, int e, int& b, int& y) {
+    auto out_index = [&](idx_t j_base, int e, int& b, int& y) -> idx_t {
         if (P.Ns == 1) {  // out[j R + y]: R contiguous elements per batch member
             b = e >> P.log2r;
             y = e & (R - 1);
@@ -220,37 +226,37 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
         // out[(j-k) R + k + y Ns]: B contiguous elements per y
         b = e & (B - 1);
         y = e >> P.log2b;
-        const int64_t j = j_base + b;
-        const int64_t k = j & (P.Ns - 1);
-        return ((j - k) << P.log2r) + k + (int64_t)y * P.Ns;
+        const idx_t j = j_base + b;
+        const idx_t k = j & ns_mask;
+        return ((j - k) << P.log2r) + k + ((idx_t)y << log2ns);
     };
 
-    for (int64_t tl = blockIdx.x; tl < num_tiles; tl += gridDim.x) {
-        const int64_t j_base = tl << P.log2b;
+    for (idx_t tl = blockIdx.x; tl < num_tiles; tl += gridDim.x) {
+        const idx_t j_base = tl << P.log2b;
         double2 v[8];
         if (active) gather(tl, v);
 
         // ---- first sub-pass (pass twiddle, radix RAD, no sub-twiddle) ----
         if (active) {
-            auto tw = [&](int64_t m) {  // W_L^m (SGN-conjugated) from the two-level table
+            auto tw = [&](idx_t m) {  // W_L^m (SGN-conjugated) from the two-level table
                 const double2 a = __ldg(P.whi + (m >> P.split));
-                const double2 bb = __ldg(P.wlo + (m & (((int64_t)1 << P.split) - 1)));
+                const double2 bb = __ldg(P.wlo + (m & (((idx_t)1 << P.split) - 1)));
                 double2 w = cmul(a, bb);
                 if (SGN > 0) w.y = -w.y;
                 return w;
             };
             const int b0 = tid & (B - 1);  // u = tid + t*T keeps the same batch member (T is a multiple of B)
-            const int64_t k = (j_base + b0) & (P.Ns - 1);
+            const idx_t k = (j_base + b0) & ns_mask;
             // element x = i + q*nbf carries W^{k x stride} = W^{k i stride} (W^{k nbf stride})^q:
             // one table lookup per butterfly plus one shared step instead of one lookup per element
             double2 wstep = make_double2(1.0, 0.0);
-            if (P.Ns > 1) wstep = tw(k * nbf * P.tw_stride);
+            if (P.Ns > 1) wstep = tw(k * (idx_t)nbf * tw_stride);
 #pragma unroll
             for (int t = 0; t < PER; t++) {
                 const int u = tid + t * T;
                 const int i = u >> P.log2b, b = u & (B - 1);
                 if (P.Ns > 1) {
-                    double2 w = tw(k * i * P.tw_stride);
+                    double2 w = tw(k * (idx_t)i * tw_stride);
 #pragma unroll
                     for (int q = 0; q < RAD; q++) {
                         v[t * RAD + q] = cmul(v[t * RAD + q], w);
@@ -305,13 +311,13 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
 #pragma unroll
             for (int t = 0; t < 8; t++) {
                 int b, y;
-                const int64_t gidx = out_index(j_base, tid + t * T, b, y);
+                const idx_t gidx = out_index(j_base, tid + t * T, b, y);
                 double2 val = S[y * pitch + b];
                 if (STORE == STORE_PLAIN) {
                     P.out[gidx] = val;
                 } else if (STORE == STORE_MULH) {
                     P.out[gidx] = cmul(val, hv[t]);
-                } else if (gidx < P.M) {
+                } else if (gidx < M32) {
                     P.spec[gidx] = cmul(val, __ldg(P.chirp + gidx));
                 }
             }
@@ -321,7 +327,7 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
 }
 
 template <int SGN, int LOAD, int STORE, int LOG2TILE>
-__global__ void __launch_bounds__((1 << LOG2TILE) / 8, LOG2TILE == kLog2TileSmall ? (STORE == STORE_MULH ? 5 : 7) : (STORE == STORE_MULH ? 2 : 3))
+__global__ void __launch_bounds__((1 << LOG2TILE) / 8, LOG2TILE == kLog2TileSmall ? (STORE == STORE_MULH ? 4 : 7) : (STORE == STORE_MULH ? 2 : 3))
     fft_tile_kernel(PassParams P) {
     extern __shared__ __align__(16) unsigned char fft_smem[];
     double2* S = reinterpret_cast<double2*>(fft_smem);

@@ -246,3 +246,26 @@ def test_file_to_spectrum_matches_oracle(tmp_path):
     wn_ref, inten_ref = ora.md_measure(alpha, 1.5)
     assert np.array_equal(wn, wn_ref)
     assert pointwise_rel_err(inten, inten_ref) <= 1e-8
+
+
+@pytest.mark.gpu
+def test_outcar_file_to_spectrum_matches_oracle(tmp_path):
+    """The reference's OUTCAR MD fixture (108 atoms: the rutile TiO2 supercell) -> pinned Trajectory ->
+    ARTModel spectrum, against the oracle fed with the reference reader's positions."""
+    import ramannoodle_b200 as rb
+    from ramannoodle_b200 import synthetic
+    from helpers import oracle_model, pointwise_rel_err, rel_err
+    from oracle import numpy_port as ora
+
+    path = _outcar_fixture(tmp_path)
+    with np.load(os.path.join(GOLDEN, "llzo_outcar_trajectory.npz")) as data:
+        want_positions = data["positions_ts"]
+    state = synthetic.make_model("TiO2", "art")
+    trajectory = rio.read_trajectory(path, file_format="outcar")
+    spectrum = trajectory.get_raman_spectrum(rb.ARTModel(state))
+    alpha = ora.calc_polarizabilities(oracle_model(state), want_positions)
+    assert rel_err(spectrum.polarizability_ts, alpha) <= 1e-10
+    wn, inten = spectrum.measure()
+    wn_ref, inten_ref = ora.md_measure(alpha, trajectory.timestep)
+    assert np.array_equal(wn, wn_ref)
+    assert pointwise_rel_err(inten, inten_ref) <= 1e-8

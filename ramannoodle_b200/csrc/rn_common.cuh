@@ -69,6 +69,7 @@ struct rn_model {
     int dense_max_pieces = 0;
     double alpha0[9] = {0};  // ref_polarizability + constant parts of the linear DOFs
     uint64_t ref_hash = 0;   // FNV-1a of the reference positions and lattice bytes (mask sweeps group on it)
+    uint64_t shape_hash = 0; // ... of every creation input except the weights: equal for masked copies of a model
 
     // device tables (all fp64)
     double* d_ref_wrapped = nullptr;  // (K)   apply_pbc(ref positions)
@@ -116,5 +117,10 @@ int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumula
 int launch_dense_v1(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
                     double* d_alpha, cudaStream_t stream);
 int launch_fill_alpha0(const rn_model* m, int64_t num_frames, double* d_alpha, cudaStream_t stream);
+// rn_dense_sweep.cu: spline part of 2..4 masked copies of one model with a shared projection
+bool dense_sweep_eligible(const rn_model* m);
+bool dense_sweep_compatible(const rn_model* a, const rn_model* b);
+int launch_dense_sweep(const rn_model* const* models, int count, const double* d_in, bool accumulate,
+                       int64_t num_frames, double* const* d_alpha, cudaStream_t stream);
 
 }  // namespace rn

@@ -222,6 +222,15 @@ extern "C" int rn_model_create(const double* h_ref_positions, int64_t num_atoms,
         mix(h_ref_positions, (size_t)K);
         mix(h_lattice, 9);
         m->ref_hash = h;
+        // everything but the weights
+        mix(h_ref_polarizability, 9);
+        if (num_dofs > 0) {
+            mix(h_basis, (size_t)num_dofs * (size_t)K);
+            mix(h_knots, (size_t)h_knot_off[num_dofs]);
+            mix(h_coefs, (size_t)h_coef_off[num_dofs] * 9);
+            for (int64_t j = 0; j < num_dofs; j++) h = (h ^ (uint64_t)(h_degree[j] + 1)) * 1099511628211ull;
+        }
+        m->shape_hash = h ^ ((uint64_t)flags << 56);
     }
 
     // ---- splines -> piecewise polynomials; classify linear vs dense ----

@@ -21,8 +21,9 @@
 //       that moved them to extra warps (setmaxnreg 232/40) were slower because DADDs of other
 //       warps starve behind the DMMA stream.
 //
-// Models that are not purely affine (or not TMA-eligible) are evaluated one after the other on the
-// resident positions; results are identical either way.
+// Spline models: masked copies share the projection onto the basis (rn_dense_sweep.cu: one
+// dense_kernel_tp launch, the chained-DMMA epilogue once per mask).  Anything else is evaluated one
+// model after the other on the resident positions; results agree to rounding either way.
 #include <algorithm>
 
 #include "rn_common.cuh"
@@ -388,6 +389,27 @@ extern "C" int rn_calc_polarizabilities_sweep(const rn_model* const* models, int
             if (rc == RN_OK) {
                 g += run;
                 continue;
+            }
+        }
+        // spline models: masked copies of one model share the projection onto the basis (rn_dense_sweep.cu)
+        if (g_sweep_fused && dense_sweep_eligible(models[g]) && reinterpret_cast<uintptr_t>(d_positions) % 8 == 0) {
+            int drun = 1;
+            while (g + drun < num_models && drun < 4 && dense_sweep_eligible(models[g + drun]) &&
+                   dense_sweep_compatible(models[g], models[g + drun]))
+                drun++;
+            if (drun == 3) drun = 2;  // kernels exist for 2 and 4 masks
+            if (drun >= 2) {
+                const bool has_affine = models[g]->num_linear > 0;
+                int rc = RN_OK;
+                for (int r = 0; r < drun && rc == RN_OK && has_affine; r++)
+                    rc = launch_affine(models[g + r], d_positions, true, num_frames, d_alpha_outputs[g + r], s);
+                if (rc != RN_OK) return rc;
+                rc = launch_dense_sweep(models + g, drun, d_positions, has_affine, num_frames, d_alpha_outputs + g, s);
+                if (rc != RN_OK && rc != 1) return rc;
+                if (rc == RN_OK) {
+                    g += drun;
+                    continue;
+                }
             }
         }
         int rc = rn_calc_polarizabilities(models[g], d_positions, num_frames, d_alpha_outputs[g], stream);

@@ -121,17 +121,28 @@ def test_sweep_fallback_is_the_single_model_path():
         assert np.array_equal(got[g], single)
 
 
-@pytest.mark.parametrize("kind", ["cubic", "mixed"])
-def test_spline_models_sweep(kind):
-    """Models with real spline DOFs are evaluated one after the other on the resident positions."""
-    state = synthetic.make_model("TiO2", kind, num_dofs=60)
+@pytest.mark.parametrize("structure,kind,num_dofs,count,frames", [
+    ("TiO2", "cubic", 60, 3, 700), ("TiO2", "mixed", 60, 4, 700), ("STO", "cubic", None, 4, 1300),
+    ("STO", "cubic", None, 2, 129), ("LLZO", "quadratic", 200, 5, 2500), ("TiO2", "mixed", None, 9, 300),
+    ("LLZO", "linear5", 130, 4, 20_000)])
+def test_spline_models_sweep(structure, kind, num_dofs, count, frames):
+    """Masked copies of a spline model share the projection onto the basis (dense_kernel_tp with 2 or 4
+    masks per launch, the epilogue once per mask); "mixed" models also carry linear DOFs, whose
+    affine part is written first and accumulated onto.  Odd atom counts (STO), the unit-balanced
+    schedule (short trajectories) and whole-tile schedule (20k frames) are covered."""
+    state = synthetic.make_model(structure, kind, num_dofs=num_dofs, seed=5)
     model = rb.InterpolationModel(state)
-    masks = _masks(state.num_dofs, 3, seed=17)
-    positions = synthetic.make_trajectory("TiO2", 700, seed=11)
-    want = _oracle_sweep(state, masks, positions)
-    got = model.calc_polarizabilities_masked(positions, masks)
-    for g in range(3):
-        assert rel_err(got[g], want[g]) <= ALPHA_RTOL
+    masks = _masks(state.num_dofs, count, seed=17 + count)
+    positions = synthetic.make_trajectory(structure, frames, seed=11)
+    sel = np.r_[0:min(frames, 200), max(0, frames - 200):frames]
+    want = _oracle_sweep(state, masks, positions[sel])
+    got_dev = model.calc_polarizabilities_masked(to_cuda(positions), masks).cpu().numpy()
+    got_host = model.calc_polarizabilities_masked(positions, masks)
+    for g in range(count):
+        assert rel_err(got_dev[g][sel], want[g]) <= ALPHA_RTOL
+        assert rel_err(got_host[g][sel], want[g]) <= ALPHA_RTOL
+        single = model.get_masked_model(np.flatnonzero(masks[g])).calc_polarizabilities(positions)
+        assert rel_err(got_host[g], single) <= 1e-12
 
 
 def test_sweep_of_different_models_and_chunked_host_stream():

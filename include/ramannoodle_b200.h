@@ -213,6 +213,11 @@ int rn_outcar_scan(const char* path, int64_t* num_frames, int64_t* num_atoms, do
 int rn_outcar_read(const char* path, double* h_positions, int64_t num_frames, int64_t num_atoms,
                    const double* inv_lattice, int num_threads, int wrap);
 
+/* Host-side Trajectory.__init__ wrap (dynamics/_trajectory.py:45; structure/utils.py:27:
+ * positions - positions // 1) with a thread pool: h_out[i] = h_in[i] - floor(h_in[i]), identical to
+ * numpy's result; h_out may be pinned memory, in place allowed.  num_threads <= 0: all cores. */
+int rn_host_apply_pbc(const double* h_in, double* h_out, int64_t count, int num_threads);
+
 /* Page-lock / unlock a caller-owned host buffer (cudaHostRegister) for fast transfers. */
 int rn_host_register(void* h_ptr, size_t bytes);
 int rn_host_unregister(void* h_ptr);

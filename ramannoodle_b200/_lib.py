@@ -73,6 +73,7 @@ PROTOTYPES = {
     "rn_outcar_scan": (ctypes.c_int, [ctypes.c_char_p, c_int64_p, c_int64_p, ctypes.c_void_p, ctypes.c_void_p]),
     "rn_outcar_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "rn_host_apply_pbc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     "rn_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     "rn_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
     "rn_bspline_to_pp": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,

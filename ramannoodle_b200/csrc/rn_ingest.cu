@@ -676,3 +676,31 @@ extern "C" int rn_outcar_read(const char* path, double* h_positions, int64_t num
     }
     return RN_OK;
 }
+
+// Trajectory.__init__ on a host array (dynamics/_trajectory.py:45 -> structure/utils.py:27:
+// positions - positions // 1), threaded: numpy's floor_divide runs at ~0.3 GB/s on one core, which
+// makes wrapping a 1M-frame trajectory (4.6 GB) cost far more than its evaluation on the GPU.
+// out[i] = in[i] - floor(in[i]) (identical to numpy for every finite input, -0.0, NaN and Inf);
+// out may be page-locked memory, in == out is allowed.  num_threads <= 0: all cores.
+extern "C" int rn_host_apply_pbc(const double* h_in, double* h_out, int64_t count, int num_threads) {
+    RN_CHECK_ARG(count >= 0, "count must be non-negative");
+    if (count == 0) return RN_OK;
+    RN_CHECK_ARG(h_in && h_out, "null pointer");
+    if (num_threads <= 0) num_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int64_t block = 1 << 18;  // 2 MiB of doubles per work item
+    num_threads = (int)std::min<int64_t>(num_threads, (count + block - 1) / block);
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const int64_t b0 = next.fetch_add(block);
+            if (b0 >= count) return;
+            const int64_t b1 = std::min(count, b0 + block);
+            for (int64_t i = b0; i < b1; i++) h_out[i] = h_in[i] - floor(h_in[i]);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < num_threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    return RN_OK;
+}

@@ -83,6 +83,10 @@ class Trajectory(Dynamics, Sequence):
         return out
 
     def _wrap_host(self, positions: np.ndarray, pin_memory: bool) -> np.ndarray:
+        """``apply_pbc(positions)`` into a fresh (page-locked, when a GPU is present) buffer.  float64
+        input goes through the library's threaded ``rn_host_apply_pbc`` (bit-identical to
+        ``positions - positions // 1``; numpy's ``floor_divide`` needs ~17 s for a 1M-frame,
+        192-atom trajectory), anything else through numpy."""
         wrapped = None
         if pin_memory and positions.size > 0:
             try:
@@ -91,14 +95,23 @@ class Trajectory(Dynamics, Sequence):
                 if torch.cuda.is_available():
                     owner = torch.empty(positions.shape, dtype=torch.float64, pin_memory=True)
                     wrapped = owner.numpy()
-                    np.floor_divide(positions, 1, out=wrapped)  # positions // 1
-                    np.subtract(positions, wrapped, out=wrapped)  # positions - positions // 1
                     self._pinned_owner = owner
             except (ImportError, RuntimeError):
                 wrapped = None
-        if wrapped is None:
-            wrapped = np.asarray(apply_pbc(positions), dtype=np.float64)
-        return wrapped
+                self._pinned_owner = None
+        if positions.dtype == np.float64 and positions.size > 0:
+            source = np.ascontiguousarray(positions)
+            if wrapped is None:
+                wrapped = np.empty(positions.shape, dtype=np.float64)
+            status = _lib.lib().rn_host_apply_pbc(ctypes.c_void_p(source.ctypes.data),
+                                                  ctypes.c_void_p(wrapped.ctypes.data), source.size, 0)
+            _lib.check(status, "rn_host_apply_pbc")
+            return wrapped
+        if wrapped is not None:
+            np.floor_divide(positions, 1, out=wrapped)  # positions // 1
+            np.subtract(positions, wrapped, out=wrapped)  # positions - positions // 1
+            return wrapped
+        return np.asarray(apply_pbc(positions), dtype=np.float64)
 
     @property
     def positions_ts(self) -> np.ndarray:

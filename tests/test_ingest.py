@@ -269,3 +269,27 @@ def test_outcar_file_to_spectrum_matches_oracle(tmp_path):
     wn_ref, inten_ref = ora.md_measure(alpha, trajectory.timestep)
     assert np.array_equal(wn, wn_ref)
     assert pointwise_rel_err(inten, inten_ref) <= 1e-8
+
+
+def test_host_apply_pbc_matches_numpy():
+    """``Trajectory.__init__`` wraps host arrays with the threaded ``rn_host_apply_pbc``: bit-identical
+    to ``positions - positions // 1`` (``structure/utils.py:27``) incl. -0.0, NaN, Inf, huge values."""
+    import ramannoodle_b200 as rb
+
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-3, 3, (700, 37, 3))
+    x[0, 0, :] = [-0.0, 0.0, 1.0]
+    x[0, 1, :] = [np.nan, np.inf, -np.inf]
+    x[0, 2, :] = [-1e-20, 1 - 1e-17, 2.0 ** 52 + 0.5]
+    x[0, 3, :] = [-5.0, 7.0, -1e-300]
+    with np.errstate(invalid="ignore"):
+        want = x - x // 1
+    got = rb.Trajectory(x, 1.0).positions_ts
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.array_equal(np.signbit(got), np.signbit(want))
+    # non-contiguous and non-float64 inputs
+    view = x[::2, :, ::-1]
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(rb.Trajectory(view, 1.0).positions_ts, view - view // 1, equal_nan=True)
+    ints = rng.integers(-2, 3, (5, 4, 3)).astype(np.float32)
+    assert np.array_equal(rb.Trajectory(ints, 1.0).positions_ts, ints - ints // 1)

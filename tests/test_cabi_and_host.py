@@ -32,6 +32,19 @@ def test_library_exports_every_declared_symbol():
     _lib.lib()
 
 
+def test_python_prototypes_match_header_arity():
+    """Every ctypes prototype takes as many arguments as the header's declaration (a mismatch would
+    only show up as a crash on the GPU box)."""
+    header = open(os.path.join(REPO, "include", "ramannoodle_b200.h"), encoding="utf-8").read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declarations = dict(re.findall(r"\b(rn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    assert sorted(declarations) == sorted(_lib.PROTOTYPES)
+    for name, params in declarations.items():
+        params = " ".join(params.split())
+        count = 0 if params in ("", "void") else params.count(",") + 1
+        assert count == len(_lib.PROTOTYPES[name][1]), f"{name}: header has {count} parameters"
+
+
 def test_no_cpu_fallback_without_gpu():
     """Without a CUDA device the product path must fail loudly, not fall back."""
     import torch

@@ -171,6 +171,14 @@ int rn_md_spectrum_finish(int64_t num_frames, const double* d_partial_sum, doubl
  * other bins zeroed unless accumulate != 0).  Summed over parts and residues (all-reduce) the partials
  * equal those of rn_md_spectrum_part; rn_md_spectrum_finish completes the spectrum. */
 int64_t rn_spectrum_half_length(const rn_spectrum_plan* plan);
+/* Sharding the series-energy pass (one read of the whole series) over ranks: with mode 1 the part /
+ * half entries leave the energies out; rn_series_energy_constant writes to d_out[0] the additive
+ * constant 45 (E_tr/9)/2 + 7 ((E_a+E_b+E_c)/2 + 3 (E_xy+E_yz+E_xz))/2 (spectrum/_raman.py:286-297 with
+ * spectrum/utils.py:95-124) of the difference signals n in [n_begin, n_end) of [0, S-1).  Summed over
+ * shards and added to every bin of the summed partials it restores what mode 0 computes. */
+int rn_spectrum_set_energy_mode(rn_spectrum_plan* plan, int mode);
+int rn_series_energy_constant(rn_spectrum_plan* plan, const double* d_alpha, int64_t n_begin,
+                              int64_t n_end, double* d_out, void* stream);
 int rn_md_spectrum_half(rn_spectrum_plan* plan, const double* d_alpha, int part, int residue,
                         double* d_z_out, int skip_energy, void* stream);
 int rn_md_spectrum_half_combine(rn_spectrum_plan* plan, int part, int residue, const double* d_z_res0,

@@ -54,6 +54,9 @@ PROTOTYPES = {
                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "rn_md_spectrum_half_combine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "rn_spectrum_set_energy_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "rn_series_energy_constant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                                 ctypes.c_void_p, ctypes.c_void_p]),
     "rn_md_spectrum_finish": (ctypes.c_int, [ctypes.c_int64, ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
                                              ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p]),

@@ -41,6 +41,9 @@ struct rn_spectrum_plan {
     rn_spectrum_plan* half = nullptr;
     double2* d_hhalf[2] = {nullptr, nullptr};  // H[r + 2k'], k' < L/2
     bool owns_chirp = true;
+    // 0: the part / half entries compute the series energies themselves; 1: they treat them as zero and
+    // the caller adds the constant of rn_series_energy_constant (sharded over ranks) to every bin
+    int energy_mode = 0;
 };
 
 namespace rn {
@@ -506,10 +509,11 @@ __global__ void chirp_filter_kernel(double2* __restrict__ out, const double2* __
 // Energies sum_n s_n^2 of the seven signals of measure() (MODE 0) or of one real signal (MODE 1).
 // Deterministic two-level reduction: per-block partials, then one block.
 template <int MODE>
-__global__ void __launch_bounds__(256) energy_partial_kernel(const double* __restrict__ src, int64_t M,
-                                                             double* __restrict__ partial) {
+__global__ void __launch_bounds__(256) energy_partial_kernel(const double* __restrict__ src, int64_t n_begin,
+                                                             int64_t M, double* __restrict__ partial) {
     double e[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < M; n += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t n = n_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < M;
+         n += (int64_t)gridDim.x * blockDim.x) {
         if (MODE == 0) {
             const double* a = src + n * 9;
             const double xx = a[9] - a[0], yy = a[13] - a[4], zz = a[17] - a[8];
@@ -561,6 +565,33 @@ __global__ void __launch_bounds__(256) energy_final_kernel(const double* __restr
         double v = 0;
         for (int w = 0; w < 8; w++) v += sm[w][threadIdx.x];
         energy[threadIdx.x] = v;
+    }
+}
+
+// The energies enter every bin of the orientational average as the same additive constant
+// 45 (E_tr/9)/2 + 7 ((E_a + E_b + E_c)/2 + 3 (E_xy + E_yz + E_xz))/2; this is that constant for the
+// frames the partials cover (sum it over shards, then add it to every bin).
+__global__ void __launch_bounds__(256) energy_constant_kernel(const double* __restrict__ partial, int blocks,
+                                                              double* __restrict__ out) {
+    __shared__ double sm[8][7];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+        double v = 0;
+        for (int b = threadIdx.x; b < blocks; b += 256) v += partial[(int64_t)b * 8 + q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) sm[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double e[7];
+        for (int q = 0; q < 7; q++) {
+            double v = 0;
+            for (int w = 0; w < 8; w++) v += sm[w][q];
+            e[q] = v;
+        }
+        out[0] = 2.5 * e[0] + 1.75 * (e[1] + e[2] + e[3]) + 10.5 * (e[4] + e[5] + e[6]);
     }
 }
 
@@ -990,7 +1021,7 @@ extern "C" int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, dou
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int64_t M = plan->M, L = plan->L;
 
-    energy_partial_kernel<0><<<plan->energy_blocks, 256, 0, s>>>(d_alpha, M, plan->d_partial);
+    energy_partial_kernel<0><<<plan->energy_blocks, 256, 0, s>>>(d_alpha, 0, M, plan->d_partial);
     RN_LAUNCHED();
     energy_final_kernel<<<1, 256, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
     RN_LAUNCHED();
@@ -1028,10 +1059,14 @@ extern "C" int rn_md_spectrum_part(rn_spectrum_plan* plan, const double* d_alpha
     DeviceGuard guard(plan->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int64_t M = plan->M, L = plan->L;
-    energy_partial_kernel<0><<<plan->energy_blocks, 256, 0, s>>>(d_alpha, M, plan->d_partial);
-    RN_LAUNCHED();
-    energy_final_kernel<<<1, 256, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
-    RN_LAUNCHED();
+    if (plan->energy_mode == 0) {
+        energy_partial_kernel<0><<<plan->energy_blocks, 256, 0, s>>>(d_alpha, 0, M, plan->d_partial);
+        RN_LAUNCHED();
+        energy_final_kernel<<<1, 256, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
+        RN_LAUNCHED();
+    } else {
+        RN_CUDA(cudaMemsetAsync(plan->d_energy, 0, sizeof(double) * 8, s));
+    }
     FftIo io;
     io.load = LOAD_ALPHA;
     io.src = d_alpha;
@@ -1066,8 +1101,10 @@ extern "C" int rn_md_spectrum_half(rn_spectrum_plan* plan, const double* d_alpha
     if (rc != RN_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rn_spectrum_plan* h = plan->half;
-    if (!skip_energy) {
-        energy_partial_kernel<0><<<plan->energy_blocks, 256, 0, s>>>(d_alpha, plan->M, plan->d_partial);
+    if (plan->energy_mode != 0) {
+        if (!skip_energy) RN_CUDA(cudaMemsetAsync(plan->d_energy, 0, sizeof(double) * 8, s));
+    } else if (!skip_energy) {
+        energy_partial_kernel<0><<<plan->energy_blocks, 256, 0, s>>>(d_alpha, 0, plan->M, plan->d_partial);
         RN_LAUNCHED();
         energy_final_kernel<<<1, 256, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
         RN_LAUNCHED();
@@ -1121,6 +1158,33 @@ extern "C" int rn_md_spectrum_half_combine(rn_spectrum_plan* plan, int part, int
     return RN_OK;
 }
 
+// Multi-GPU measure: the series energies (one full pass over the series) shard over ranks.  With
+// mode 1 rn_md_spectrum_part / rn_md_spectrum_half leave the energies out; rn_series_energy_constant
+// writes the additive constant contributed by the difference signals n in [n_begin, n_end) (a subset of
+// [0, S-1)) to d_out[0].  Summed over shards (it can ride as one extra element of the partial-intensity
+// all-reduce) and added to every bin it restores exactly what mode 0 computes.
+extern "C" int rn_spectrum_set_energy_mode(rn_spectrum_plan* plan, int mode) {
+    RN_CHECK_ARG(plan != nullptr, "plan is null");
+    RN_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 or 1");
+    plan->energy_mode = mode;
+    return RN_OK;
+}
+
+extern "C" int rn_series_energy_constant(rn_spectrum_plan* plan, const double* d_alpha, int64_t n_begin,
+                                         int64_t n_end, double* d_out, void* stream) {
+    RN_CHECK_ARG(plan != nullptr && d_alpha != nullptr && d_out != nullptr, "null pointer");
+    RN_CHECK_ARG(n_begin >= 0 && n_begin <= n_end && n_end <= plan->M, "invalid range [%lld, %lld) of %lld",
+                 (long long)n_begin, (long long)n_end, (long long)plan->M);
+    DeviceGuard guard(plan->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    energy_partial_kernel<0><<<plan->energy_blocks, 256, 0, s>>>(d_alpha, n_begin, n_end, plan->d_partial);
+    RN_LAUNCHED();
+    energy_constant_kernel<<<1, 256, 0, s>>>(plan->d_partial, plan->energy_blocks, d_out);
+    RN_LAUNCHED();
+    RN_CUDA(cudaGetLastError());
+    return RN_OK;
+}
+
 extern "C" int rn_md_spectrum_finish(int64_t num_frames, const double* d_partial_sum, double timestep_fs,
                                      int laser_correction, double laser_wavelength_nm, int bose_einstein_correction,
                                      double temperature_K, double* d_wavenumbers, double* d_intensities, void* stream) {
@@ -1152,7 +1216,7 @@ extern "C" int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int64_t M = plan->M, L = plan->L;
     const int64_t points = (M + 1) / 2;
-    energy_partial_kernel<1><<<plan->energy_blocks, 256, 0, s>>>(d_signal, M, plan->d_partial);
+    energy_partial_kernel<1><<<plan->energy_blocks, 256, 0, s>>>(d_signal, 0, M, plan->d_partial);
     RN_LAUNCHED();
     energy_final_kernel<<<1, 256, 0, s>>>(plan->d_partial, plan->energy_blocks, plan->d_energy);
     RN_LAUNCHED();

@@ -204,23 +204,41 @@ class ShardedMDRamanSpectrum(MDRamanSpectrum):
         world, rank = dist.get_world_size(self._group), dist.get_rank(self._group)
         points = int(_lib.lib().rn_spectrum_num_points(num_frames))
         with torch.cuda.device(device):
-            total = torch.zeros(points, dtype=torch.float64, device=series.device)
+            # element `points` of the reduced vector carries the sharded series-energy constant
+            total = torch.zeros(points + 1, dtype=torch.float64, device=series.device)
             wavenumbers = torch.empty(points, dtype=torch.float64, device=series.device)
             intensities = torch.empty(points, dtype=torch.float64, device=series.device)
             if points > 0:
                 plan = _get_plan(num_frames, device)
-                split = world > 1 and self._measure_split(series, plan, total, world, rank, device)
-                parts = [] if split else spectrum_parts(world, rank)
-                if parts:
-                    partial = torch.empty(points, dtype=torch.float64, device=series.device)
-                    for part in parts:
-                        status = _lib.lib().rn_md_spectrum_part(plan.handle, ctypes.c_void_p(series.data_ptr()), part,
-                                                                ctypes.c_void_p(partial.data_ptr()), _stream(device))
-                        _lib.check(status, "rn_md_spectrum_part")
-                        total += partial
+                lib = _lib.lib()
+                # the energies (one pass over the whole series) shard over ranks: every rank sums the
+                # difference signals of its block and the constant rides along with the all-reduce
+                shard_energy = world > 1
+                if shard_energy:
+                    _lib.check(lib.rn_spectrum_set_energy_mode(plan.handle, 1), "rn_spectrum_set_energy_mode")
+                try:
+                    split = world > 1 and self._measure_split(series, plan, total, world, rank, device)
+                    parts = [] if split else spectrum_parts(world, rank)
+                    if parts:
+                        partial = torch.empty(points, dtype=torch.float64, device=series.device)
+                        for part in parts:
+                            status = lib.rn_md_spectrum_part(plan.handle, ctypes.c_void_p(series.data_ptr()), part,
+                                                             ctypes.c_void_p(partial.data_ptr()), _stream(device))
+                            _lib.check(status, "rn_md_spectrum_part")
+                            total[:points] += partial
+                    if shard_energy:
+                        begin, end = shard_bounds(num_frames - 1, world, rank)
+                        status = lib.rn_series_energy_constant(
+                            plan.handle, ctypes.c_void_p(series.data_ptr()), begin, end,
+                            ctypes.c_void_p(total.data_ptr() + 8 * points), _stream(device))
+                        _lib.check(status, "rn_series_energy_constant")
+                finally:
+                    if shard_energy:
+                        lib.rn_spectrum_set_energy_mode(plan.handle, 0)
                 if world > 1:
                     dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self._group)
-                status = _lib.lib().rn_md_spectrum_finish(
+                    total[:points] += total[points]
+                status = lib.rn_md_spectrum_finish(
                     num_frames, ctypes.c_void_p(total.data_ptr()), float(self._timestep),
                     1 if laser_correction else 0, float(laser_wavelength) if laser_correction else 0.0,
                     1 if bose_einstein_correction else 0, float(temperature) if bose_einstein_correction else 0.0,

@@ -266,3 +266,61 @@ def test_split_transforms_sum_to_measure(frames):
     assert lib.rn_md_spectrum_finish(frames, ptr(total), 1.5, 1, 532.0, 0, 0.0, ptr(wn), ptr(inten), stream) == 0
     assert np.array_equal(wn.cpu().numpy(), ref_wn)
     assert pointwise_rel_err(inten.cpu().numpy(), ref_inten) <= INTENSITY_RTOL
+
+
+@pytest.mark.parametrize("frames", [41, 4097, 120_001])
+def test_sharded_energy_constant(frames):
+    """Energy mode 1 (multi-GPU measure): parts and half transforms without the series energies plus
+    the constants of three frame shards (rn_series_energy_constant) equal the default computation."""
+    import ctypes
+
+    from ramannoodle_b200 import _lib
+    from ramannoodle_b200.distributed import shard_bounds
+    from ramannoodle_b200.spectrum import _get_plan
+
+    rng = np.random.default_rng(frames + 7)
+    alpha = 6.0 * np.eye(3)[None] + 0.02 * rng.normal(size=(frames, 3, 3)).cumsum(axis=0) / np.sqrt(frames)
+    d_alpha = to_cuda(alpha)
+    lib = _lib.lib()
+    plan = _get_plan(frames, 0)
+    points = int(lib.rn_spectrum_num_points(frames))
+    half = int(lib.rn_spectrum_half_length(plan.handle))
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+
+    def parts_total():
+        total = torch.zeros(points, dtype=torch.float64, device="cuda:0")
+        piece = torch.empty_like(total)
+        for part in range(3):
+            assert lib.rn_md_spectrum_part(plan.handle, ptr(d_alpha), part, ptr(piece), stream) == 0
+            total += piece
+        return total
+
+    def halves_total():
+        total = torch.zeros(points, dtype=torch.float64, device="cuda:0")
+        z = torch.empty((2, half, 2), dtype=torch.float64, device="cuda:0")
+        for part in range(3):
+            for residue in range(2):
+                assert lib.rn_md_spectrum_half(plan.handle, ptr(d_alpha), part, residue, ptr(z[residue]),
+                                               0 if (part == 0 and residue == 0) else 1, stream) == 0
+            for residue in range(2):
+                assert lib.rn_md_spectrum_half_combine(plan.handle, part, residue, ptr(z[0]), ptr(z[1]), ptr(total), 1,
+                                                       stream) == 0
+        return total
+
+    want = parts_total()
+    assert lib.rn_spectrum_set_energy_mode(plan.handle, 1) == 0
+    try:
+        bare_parts = parts_total()
+        bare_halves = halves_total()
+        constant = torch.zeros(3, dtype=torch.float64, device="cuda:0")
+        for rank in range(3):
+            begin, end = shard_bounds(frames - 1, 3, rank)
+            assert lib.rn_series_energy_constant(plan.handle, ptr(d_alpha), begin, end, ptr(constant[rank:]), stream) == 0
+    finally:
+        assert lib.rn_spectrum_set_energy_mode(plan.handle, 0) == 0
+    shift = constant.sum()
+    assert float(shift) > 0
+    assert rel_err((bare_parts + shift).cpu().numpy(), want.cpu().numpy()) <= 1e-12
+    assert rel_err((bare_halves + shift).cpu().numpy(), want.cpu().numpy()) <= 1e-12
+    assert rel_err(parts_total().cpu().numpy(), want.cpu().numpy()) == 0.0  # mode restored

@@ -257,12 +257,25 @@ __device__ __forceinline__ void fft_tile_body(const PassParams& P, double2* S) {
             // one table lookup per butterfly plus one shared step instead of one lookup per element
             double2 wstep = make_double2(1.0, 0.0);
             if (P.Ns > 1) wstep = tw(k * (idx_t)nbf * tw_stride);
+            // butterflies t = 0..PER-1 of a thread sit at i_t = i_0 + t (T >> log2b): their twiddles are
+            // W^{k i_0 stride} (W^{k (T >> log2b) stride})^t — with PER > 2 one more lookup replaces PER - 1
+            double2 wt_base = make_double2(1.0, 0.0), wt_step = make_double2(1.0, 0.0);
+            if (PER > 2 && P.Ns > 1) {
+                wt_base = tw(k * (idx_t)(tid >> P.log2b) * tw_stride);
+                wt_step = tw(k * (idx_t)(T >> P.log2b) * tw_stride);
+            }
 #pragma unroll
             for (int t = 0; t < PER; t++) {
                 const int u = tid + t * T;
                 const int i = u >> P.log2b, b = u & (B - 1);
                 if (P.Ns > 1) {
-                    double2 w = tw(k * (idx_t)i * tw_stride);
+                    double2 w;
+                    if (PER > 2) {
+                        w = wt_base;
+                        if (t + 1 < PER) wt_base = cmul(wt_base, wt_step);
+                    } else {
+                        w = tw(k * (idx_t)i * tw_stride);
+                    }
 #pragma unroll
                     for (int q = 0; q < RAD; q++) {
                         v[t * RAD + q] = cmul(v[t * RAD + q], w);

@@ -475,6 +475,97 @@ static int scan_outcar_frames(const MappedFile& f, const OutcarHeader& h, std::v
     return RN_OK;
 }
 
+// Threaded frame scan for regular files: every thread walks the lines of its byte range and notes the
+// lines that start with D/d (coordinate lines start with blanks, digits or a sign, never a letter).
+// The result is accepted only if it is exactly what the sequential reference walk would produce —
+// first label right after the header, labels exactly N+1 lines apart, N complete lines after the last
+// one, nothing but blank lines behind them; anything else (selective dynamics, Cartesian frames,
+// blank or extra lines in between) is left to scan_frames, which follows the reference line by line.
+static bool scan_frames_parallel(const MappedFile& f, const XdatcarHeader& h, std::vector<size_t>& starts,
+                                 int num_threads) {
+    const size_t begin = h.frames_begin;
+    if (begin >= f.size || num_threads < 2) return false;
+    const size_t span = f.size - begin;
+    if (span < ((size_t)8 << 20)) return false;
+    num_threads = (int)std::min<size_t>((size_t)num_threads, span >> 20);
+    struct Chunk {
+        std::vector<size_t> first_coord;  // offset of the line after each label line
+        std::vector<int64_t> label_line;  // line index (within the chunk) of each label line
+        int64_t lines = 0;                // lines starting in this chunk
+        bool odd = false;                 // a line starting with a letter other than D/d
+    };
+    std::vector<Chunk> chunks((size_t)num_threads);
+    auto work = [&](int t) {
+        Chunk& c = chunks[(size_t)t];
+        size_t lo = begin + span * (size_t)t / (size_t)num_threads;
+        const size_t hi = begin + span * (size_t)(t + 1) / (size_t)num_threads;
+        if (t > 0) {  // first line that starts at or after lo
+            const void* nl = memchr(f.data + lo - 1, '\n', f.size - (lo - 1));
+            if (!nl) return;
+            lo = (size_t)(static_cast<const char*>(nl) - f.data) + 1;
+        }
+        size_t pos = lo, end = 0;
+        while (pos < hi && pos < f.size) {
+            const char ch = f.data[pos];
+            const size_t next = next_line(f.data, f.size, pos, &end);
+            if (ch == 'D' || ch == 'd') {
+                c.first_coord.push_back(next);
+                c.label_line.push_back(c.lines);
+            } else if ((ch >= 'A' && ch <= 'Z') || (ch >= 'a' && ch <= 'z')) {
+                c.odd = true;
+            }
+            c.lines++;
+            pos = next;
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < num_threads; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+    }
+    // stitch and verify
+    int64_t base = 0, prev_label = -1, total_lines = 0;
+    size_t count = 0;
+    for (const Chunk& c : chunks) {
+        if (c.odd) return false;
+        count += c.label_line.size();
+        total_lines += c.lines;
+    }
+    if (count == 0) return false;
+    starts.clear();
+    starts.reserve(count);
+    for (const Chunk& c : chunks) {
+        for (size_t i = 0; i < c.label_line.size(); i++) {
+            const int64_t line = base + c.label_line[i];
+            if (prev_label < 0 ? line != 0 : line != prev_label + h.num_atoms + 1) {
+                starts.clear();
+                return false;
+            }
+            prev_label = line;
+            starts.push_back(c.first_coord[i]);
+        }
+        base += c.lines;
+    }
+    // the last frame must be complete; whatever follows it must be blank lines (the reference stops there)
+    if (total_lines < prev_label + 1 + h.num_atoms) {
+        starts.clear();
+        return false;
+    }
+    size_t pos = starts.back(), end = 0;
+    for (int64_t a = 0; a < h.num_atoms; a++) pos = next_line(f.data, f.size, pos, &end);
+    while (pos < f.size) {
+        const size_t line = pos;
+        pos = next_line(f.data, f.size, pos, &end);
+        for (size_t i = line; i < end; i++)
+            if (f.data[i] != ' ' && f.data[i] != '\t' && f.data[i] != '\r') {
+                starts.clear();
+                return false;
+            }
+    }
+    return true;
+}
+
 // rn_xdatcar_scan is always followed by rn_xdatcar_read on the same file: keep the last frame index
 // so the newline pass runs once (keyed by path, size and mtime).
 struct FrameIndex {
@@ -505,8 +596,11 @@ static int index_file(const char* path, const MappedFile& f, XdatcarHeader& h, s
     }
     int rc = parse_header(f, h);
     if (rc != RN_OK) return rc;
-    rc = scan_frames(f, h, starts);
-    if (rc != RN_OK) return rc;
+    if (!scan_frames_parallel(f, h, starts, (int)std::max(1u, std::thread::hardware_concurrency()))) {
+        starts.clear();
+        rc = scan_frames(f, h, starts);
+        if (rc != RN_OK) return rc;
+    }
     if (!consume) {
         std::lock_guard<std::mutex> lock(g_index_mutex);
         g_index.path = path;

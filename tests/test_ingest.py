@@ -293,3 +293,33 @@ def test_host_apply_pbc_matches_numpy():
         assert np.array_equal(rb.Trajectory(view, 1.0).positions_ts, view - view // 1, equal_nan=True)
     ints = rng.integers(-2, 3, (5, 4, 3)).astype(np.float32)
     assert np.array_equal(rb.Trajectory(ints, 1.0).positions_ts, ints - ints // 1)
+
+
+def test_parallel_frame_scan_keeps_reference_semantics(tmp_path):
+    """Files above 8 MB take the threaded frame scan when they are perfectly regular; trailing blank
+    lines are fine, anything irregular falls back to the line-by-line walk of the reference
+    (``xdatcar.py:33-56``): a blank label line ends the series, a truncated last frame is an error."""
+    rng = np.random.default_rng(9)
+    frames, atoms = 800, 400
+    positions = np.round(rng.random((frames, atoms, 3)), 8)
+
+    def write(path, blank_at=None, tail=""):
+        with open(path, "w", encoding="utf-8") as fh:
+            fh.write("t\\n 1.0\\n 10 0 0\\n 0 10 0\\n 0 0 10\\n A B\\n 200 200\\n")
+            for s in range(frames):
+                if s == blank_at:
+                    fh.write("\\n")
+                fh.write(f"Direct configuration= {s + 1:5d}\\n")
+                fh.write("".join(f"  {a:.8f}  {b:.8f}  {c:.8f}\\n" for a, b, c in positions[s]))
+            fh.write(tail)
+
+    write(tmp_path / "regular")
+    assert os.path.getsize(tmp_path / "regular") > (8 << 20)
+    assert np.array_equal(rio.read_positions_ts(tmp_path / "regular"), positions)
+    write(tmp_path / "tail", tail="\\n  \\n\\n")
+    assert np.array_equal(rio.read_positions_ts(tmp_path / "tail"), positions)
+    write(tmp_path / "blank", blank_at=500)
+    assert np.array_equal(rio.read_positions_ts(tmp_path / "blank"), positions[:500])
+    write(tmp_path / "truncated", tail="Direct configuration=   801\\n  0.1 0.2 0.3\\n")
+    with pytest.raises(rio.InvalidFileException, match="file ends inside frame 801"):
+        rio.read_positions_ts(tmp_path / "truncated")

@@ -305,21 +305,23 @@ def test_parallel_frame_scan_keeps_reference_semantics(tmp_path):
 
     def write(path, blank_at=None, tail=""):
         with open(path, "w", encoding="utf-8") as fh:
-            fh.write("t\\n 1.0\\n 10 0 0\\n 0 10 0\\n 0 0 10\\n A B\\n 200 200\\n")
+            fh.write("t\n 1.0\n 10 0 0\n 0 10 0\n 0 0 10\n A B\n 200 200\n")
             for s in range(frames):
                 if s == blank_at:
-                    fh.write("\\n")
-                fh.write(f"Direct configuration= {s + 1:5d}\\n")
-                fh.write("".join(f"  {a:.8f}  {b:.8f}  {c:.8f}\\n" for a, b, c in positions[s]))
+                    fh.write("\n")
+                fh.write(f"Direct configuration= {s + 1:5d}\n")
+                fh.write("".join(f"  {a:.8f}  {b:.8f}  {c:.8f}\n" for a, b, c in positions[s]))
             fh.write(tail)
 
     write(tmp_path / "regular")
     assert os.path.getsize(tmp_path / "regular") > (8 << 20)
-    assert np.array_equal(rio.read_positions_ts(tmp_path / "regular"), positions)
-    write(tmp_path / "tail", tail="\\n  \\n\\n")
-    assert np.array_equal(rio.read_positions_ts(tmp_path / "tail"), positions)
+    want = _python_parse(tmp_path / "regular", atoms)  # float() of every token, as the reference parses
+    assert want.shape == positions.shape and np.allclose(want, positions, rtol=0, atol=1e-15)
+    assert np.array_equal(rio.read_positions_ts(tmp_path / "regular"), want)
+    write(tmp_path / "tail", tail="\n  \n\n")
+    assert np.array_equal(rio.read_positions_ts(tmp_path / "tail"), want)
     write(tmp_path / "blank", blank_at=500)
-    assert np.array_equal(rio.read_positions_ts(tmp_path / "blank"), positions[:500])
-    write(tmp_path / "truncated", tail="Direct configuration=   801\\n  0.1 0.2 0.3\\n")
+    assert np.array_equal(rio.read_positions_ts(tmp_path / "blank"), want[:500])
+    write(tmp_path / "truncated", tail="Direct configuration=   801\n  0.1 0.2 0.3\n")
     with pytest.raises(rio.InvalidFileException, match="file ends inside frame 801"):
         rio.read_positions_ts(tmp_path / "truncated")

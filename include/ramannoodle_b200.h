@@ -135,8 +135,9 @@ int rn_apply_pbc(const double* d_in, double* d_out, int64_t count, void* stream)
  * MD Raman spectrum — replaces MDRamanSpectrum.measure (spectrum/_raman.py:241-309) with
  * calc_signal_spectrum (spectrum/utils.py:95-124) evaluated through the identity
  *   Re FFT_M(autocorr+(x))[k] = (|FFT_M(x)[k]|^2 + sum x^2) / 2,  M = S - 1,
- * using an arbitrary-length (Bluestein) FFT written for this library.
- * A plan owns the FFT work buffers for one series length S on one device.
+ * using an arbitrary-length (Bluestein) FFT written for this library (in-place DIF/DIT convolution,
+ * csrc/rn_fft.cuh).  A plan owns the tables and work buffers for one series length S on one device;
+ * calls on one plan must not overlap (one stream at a time).
  * ------------------------------------------------------------------------------------ */
 int rn_spectrum_plan_create(int64_t num_frames, int device, rn_spectrum_plan** out);
 int rn_spectrum_plan_destroy(rn_spectrum_plan* plan);
@@ -147,42 +148,45 @@ int64_t rn_spectrum_num_points(int64_t num_frames);
 int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, double timestep_fs,
                    int laser_correction, double laser_wavelength_nm, int bose_einstein_correction,
                    double temperature_K, double* d_wavenumbers, double* d_intensities, void* stream);
-/* Sharded form of rn_md_spectrum for multi-GPU runs (one process per GPU).  The orientational
- * average of _raman.py:286-297 is a sum of three independent packed transforms ("parts": 0 =
- * anisotropy differences, 1 = trace + xy, 2 = yz + xz); rn_md_spectrum_part writes the
- * uncorrected contribution of one part to d_partial (P,), parts from different ranks are summed
- * (all-reduce), and rn_md_spectrum_finish turns the sum into (wavenumbers, intensities) with the
- * optional corrections.  part 0 + part 1 + part 2 followed by finish == rn_md_spectrum. */
-int rn_md_spectrum_part(rn_spectrum_plan* plan, const double* d_alpha, int part, double* d_partial,
-                        void* stream);
-int rn_md_spectrum_finish(int64_t num_frames, const double* d_partial_sum, double timestep_fs,
-                          int laser_correction, double laser_wavelength_nm,
-                          int bose_einstein_correction, double temperature_K, double* d_wavenumbers,
-                          double* d_intensities, void* stream);
-
-/* A packed transform split over TWO ranks (multi-GPU measure with 2 or >= 6 ranks): the chirp-z
- * input is zero beyond M <= L/2, so the length-L transform separates by output residue r = k mod 2
- * into two length-L/2 transforms.  rn_md_spectrum_half runs residue `residue` (0/1) of part `part`
- * and writes its length-L/2 inverse transform (rn_spectrum_half_length(plan) complex doubles) to
- * d_z_out — memory the partner rank can read (symmetric memory over NVLink); skip_energy != 0
- * reuses the series energies a previous call on the same plan and series computed.
- * rn_md_spectrum_half_combine then finishes the half of the bins this residue owns from both
- * residues' buffers (d_z_res0 / d_z_res1: one local, one the partner's) into d_partial (P doubles;
- * other bins zeroed unless accumulate != 0).  Summed over parts and residues (all-reduce) the partials
- * equal those of rn_md_spectrum_part; rn_md_spectrum_finish completes the spectrum. */
-int64_t rn_spectrum_half_length(const rn_spectrum_plan* plan);
-/* Sharding the series-energy pass (one read of the whole series) over ranks: with mode 1 the part /
- * half entries leave the energies out; rn_series_energy_constant writes to d_out[0] the additive
- * constant 45 (E_tr/9)/2 + 7 ((E_a+E_b+E_c)/2 + 3 (E_xy+E_yz+E_xz))/2 (spectrum/_raman.py:286-297 with
- * spectrum/utils.py:95-124) of the difference signals n in [n_begin, n_end) of [0, S-1).  Summed over
- * shards and added to every bin of the summed partials it restores what mode 0 computes. */
-int rn_spectrum_set_energy_mode(rn_spectrum_plan* plan, int mode);
-int rn_series_energy_constant(rn_spectrum_plan* plan, const double* d_alpha, int64_t n_begin,
-                              int64_t n_end, double* d_out, void* stream);
-int rn_md_spectrum_half(rn_spectrum_plan* plan, const double* d_alpha, int part, int residue,
-                        double* d_z_out, int skip_energy, void* stream);
-int rn_md_spectrum_half_combine(rn_spectrum_plan* plan, int part, int residue, const double* d_z_res0,
-                                const double* d_z_res1, double* d_partial, int accumulate, void* stream);
+/* One transform shared by the ranks of a multi-GPU run (one process per GPU; no reference
+ * counterpart — same result as rn_md_spectrum on the whole series).  The chirp-z transform of
+ * length L is decimated in frequency over the G = 2, 4 or 8 ranks of the group (the largest power
+ * of two <= world; further ranks only receive the result):
+ *   1. the evaluation kernels store every series row n to the rank whose block of n' = n mod (L/G)
+ *      contains it (rn_spectrum_dist_route: owner(n) = (n mod period) / width; a rank also needs row
+ *      n+1 of its last n) — rn_calc_polarizabilities_routed;
+ *   2. rn_spectrum_dist_pack: np.diff, signal packing, chirp pre-multiply, G-point DFT over the blocks
+ *      and twiddle for this rank's n'; residue r is stored into peer_work[r] (rank r's work buffer);
+ *   3. rn_spectrum_dist_transform: the local length-L/G convolution with this rank's decimated
+ *      filter, in place in d_work; its last pass stores every value to the rank that owns that m'
+ *      (peer_recv[owner]);
+ *   4. rn_spectrum_dist_final: the G-point inverse DFT over the residues for this rank's m', and
+ *      P[m] = sum_p |y_p[m]|^2 (plus this rank's share of the series energy) stored to every
+ *      destination's power buffer;
+ *   5. rn_spectrum_dist_combine (every rank): I[k] = (P[k] + P[M-k]) / (4 L^2) + E/2, wavenumbers and
+ *      the optional corrections — exactly what rn_md_spectrum returns.
+ * The caller separates the steps with a cross-rank barrier (the buffers are peer-mapped device memory,
+ * e.g. symmetric memory over NVLink) and provides, per rank, a work buffer, a receive buffer and a
+ * power buffer of rn_spectrum_dist_sizes bytes.  All ranks of the world call every step; for spectator
+ * ranks (rank >= G) steps 2-4 return immediately. */
+int rn_spectrum_plan_create_dist(int64_t num_frames, int device, int world, int rank,
+                                 rn_spectrum_plan** out);
+/* info[0]=log2 L, [1]=ranks sharing the transform, [2]=log2 of the local length, [3]=strided levels,
+ * [4],[5]=log2 of their radices, [6]=block of n' / m' one rank owns, [7]=M. */
+int rn_spectrum_plan_info(const rn_spectrum_plan* plan, int64_t info[8]);
+int rn_spectrum_dist_sizes(const rn_spectrum_plan* plan, int64_t* work_bytes, int64_t* recv_bytes,
+                           int64_t* power_bytes);
+int rn_spectrum_dist_route(const rn_spectrum_plan* plan, int64_t* period, int64_t* width);
+int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_series, double* const* peer_work,
+                          void* stream);
+int rn_spectrum_dist_transform(rn_spectrum_plan* plan, double* d_work, double* const* peer_recv,
+                               void* stream);
+int rn_spectrum_dist_final(rn_spectrum_plan* plan, const double* d_recv, double* const* dest_power,
+                           int num_dest, void* stream);
+int rn_spectrum_dist_combine(const rn_spectrum_plan* plan, const double* d_power, double timestep_fs,
+                             int laser_correction, double laser_wavelength_nm,
+                             int bose_einstein_correction, double temperature_K,
+                             double* d_wavenumbers, double* d_intensities, void* stream);
 /* calc_signal_spectrum(signal, sampling_rate) (spectrum/utils.py:95-124) for one real signal of
  * length M = S-1 of the plan: outputs ceil(M/2) points (bin 0 included). */
 int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal, double sampling_rate,

@@ -47,19 +47,18 @@ PROTOTYPES = {
     "rn_md_spectrum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
                                       ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p]),
-    "rn_md_spectrum_part": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
-                                           ctypes.c_void_p]),
-    "rn_spectrum_half_length": (ctypes.c_int64, [ctypes.c_void_p]),
-    "rn_md_spectrum_half": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
-                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
-    "rn_md_spectrum_half_combine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
-    "rn_spectrum_set_energy_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
-    "rn_series_energy_constant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
-                                                 ctypes.c_void_p, ctypes.c_void_p]),
-    "rn_md_spectrum_finish": (ctypes.c_int, [ctypes.c_int64, ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
-                                             ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
-                                             ctypes.c_void_p, ctypes.c_void_p]),
+    "rn_spectrum_plan_create_dist": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.POINTER(ctypes.c_void_p)]),
+    "rn_spectrum_plan_info": (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
+    "rn_spectrum_dist_sizes": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, c_int64_p, c_int64_p]),
+    "rn_spectrum_dist_route": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, c_int64_p]),
+    "rn_spectrum_dist_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "rn_spectrum_dist_transform": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "rn_spectrum_dist_final": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                              ctypes.c_void_p]),
+    "rn_spectrum_dist_combine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
+                                                ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_void_p]),
     "rn_signal_spectrum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p]),
     "rn_convolve_workspace_size": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int64]),
@@ -84,6 +83,18 @@ PROTOTYPES = {
     "rn_launch_count": (ctypes.c_int64, []),
 }
 
+# test / tuning hooks: include/ramannoodle_b200_debug.h
+DEBUG_PROTOTYPES = {
+    "rn_debug_force_generic_affine": (None, [ctypes.c_int]),
+    "rn_debug_set_affine_config": (None, [ctypes.c_int, ctypes.c_int]),
+    "rn_debug_set_dense_config": (None, [ctypes.c_int, ctypes.c_int]),
+    "rn_debug_set_dense_split": (None, [ctypes.c_int]),
+    "rn_debug_set_sweep_fused": (None, [ctypes.c_int]),
+    "rn_debug_set_sweep_min_run": (None, [ctypes.c_int]),
+    "rn_debug_fft_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "rn_debug_fft_convolve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+}
+
 _lib = None
 
 
@@ -106,8 +117,10 @@ def lib() -> ctypes.CDLL:
                 raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from exc
             fn.restype = restype
             fn.argtypes = argtypes
-        handle.rn_debug_force_generic_affine.restype = None
-        handle.rn_debug_force_generic_affine.argtypes = [ctypes.c_int]
+        for name, (restype, argtypes) in DEBUG_PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
         _lib = handle
     return _lib
 

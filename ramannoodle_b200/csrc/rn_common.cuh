@@ -100,13 +100,43 @@ struct rn_model {
 
 namespace rn {
 
-// Extra destinations of the polarizability series: the same rows are stored to every pointer
-// (peer GPUs' buffers mapped over NVLink) by the kernel itself — the all-gather is fused into the
-// evaluation.  Pointers are pre-offset to this rank's first frame.
+// Extra destinations of the polarizability series, written by the evaluation kernels themselves over
+// NVLink (peer-mapped device memory).
+//   broadcast (log2_period < 0): the rows are stored to ptr[0..count) — every pointer pre-offset to this
+//     rank's first frame (fused all-gather);
+//   routed (log2_period >= 0): ptr[r] is rank r's full (S,3,3) series buffer (null for this rank itself or
+//     for ranks that own nothing); row n (global index first_frame + local row) goes to the ranks
+//     owner(n) and owner(n-1), owner(n) = (n mod 2^log2_period) >> log2_width — the rank whose spectrum
+//     stage consumes the difference signal n needs rows n and n+1 (rn_spectrum_dist_route).
 struct AlphaPeers {
-    double* ptr[7];
+    double* ptr[8];
     int count;
+    int log2_period;
+    int log2_width;
+    int64_t first_frame;
 };
+
+// bit r set: rows [local_row, local_row + rows) go to ptr[r] (rows <= 2^log2_width: at most two owners)
+__host__ __device__ inline uint32_t alpha_peer_mask(const AlphaPeers& P, int64_t local_row, int rows) {
+    if (P.log2_period < 0) return (1u << P.count) - 1u;
+    const int64_t n0 = P.first_frame + local_row;
+    const int64_t period_mask = ((int64_t)1 << P.log2_period) - 1;
+    const int64_t a = n0 > 0 ? n0 - 1 : 0, b = n0 + rows - 1;
+    return (1u << (int)((a & period_mask) >> P.log2_width)) | (1u << (int)((b & period_mask) >> P.log2_width));
+}
+inline AlphaPeers no_peers() {
+    AlphaPeers p;
+    for (int i = 0; i < 8; i++) p.ptr[i] = nullptr;
+    p.count = 0;
+    p.log2_period = -1;
+    p.log2_width = 0;
+    p.first_frame = 0;
+    return p;
+}
+// offset (doubles) of local row `local_row` in destination r
+__host__ __device__ inline int64_t alpha_peer_offset(const AlphaPeers& P, int64_t local_row) {
+    return (P.log2_period < 0 ? local_row : P.first_frame + local_row) * 9;
+}
 
 // kernels / launchers implemented in rn_polarizability.cu / rn_dense.cu.  `peers` may be null;
 // *peers_done is set when the launched kernel stored to the peers itself.

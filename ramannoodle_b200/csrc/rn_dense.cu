@@ -26,8 +26,9 @@ namespace rn {
 
 // A/B hook (rn_debug_set_dense_config): generation 1 = rn_polarizability.cu, 3 = warp-specialised with
 // the piecewise-polynomial epilogue, 4 = warp-specialised with the chained-DMMA epilogue (default)
-static int g_dense_version = 4;
-static int g_dense_split = 1;  // 0 = never, 1 = when whole tiles would leave SMs idle, 2 = always (tests)
+// A/B switches (include/ramannoodle_b200_debug.h): atomics, read once per launch
+static std::atomic<int> g_dense_version{4};
+static std::atomic<int> g_dense_split{1};  // 0 = never, 1 = when whole tiles would leave SMs idle, 2 = always (tests)
 
 // ------------------------------------------------------------------------------------
 // Third generation: warp-specialised.  Warps 0-3 only issue LDS + DMMA (one MMA warp per
@@ -265,8 +266,9 @@ static int launch_tp_cfg(const rn_model* m, const double* d_in, bool wrap, bool 
     // Not used with fused peer stores (the peers need finished rows).
     const int64_t jtiles = m->dense_pad / kJT2;
     const int64_t rounds = (tiles + m->sm_count - 1) / m->sm_count;
-    const bool split = g_dense_split != 0 && peers.count == 0 && tiles * jtiles >= 2 &&
-                       (g_dense_split == 2 || (double)(rounds * m->sm_count) > 1.04 * (double)tiles);
+    const int split_mode = g_dense_split.load(std::memory_order_relaxed);
+    const bool split = split_mode != 0 && peers.count == 0 && tiles * jtiles >= 2 &&
+                       (split_mode == 2 || (double)(rounds * m->sm_count) > 1.04 * (double)tiles);
     if (split) {
         grid = (int)std::min<int64_t>(tiles * jtiles, m->sm_count);
         if (!accumulate) {
@@ -365,11 +367,11 @@ int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumula
                  double* d_alpha, cudaStream_t stream, const AlphaPeers* peers, bool* peers_done) {
     if (num_frames == 0) return RN_OK;
     int rc = 1;
-    AlphaPeers fused;
-    fused.count = 0;
+    AlphaPeers fused = no_peers();
     if (peers) fused = *peers;
     if (peers_done) *peers_done = false;
-    if (g_dense_version == 4 && m->tp_mode != 0 && m->tp_features <= 12) {
+    const int dense_version = g_dense_version.load(std::memory_order_relaxed);
+    if (dense_version == 4 && m->tp_mode != 0 && m->tp_features <= 12) {
         switch (m->dense_degree) {
             case 1: rc = launch_tp_deg<1>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, fused); break;
             case 2: rc = launch_tp_deg<2>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream, fused); break;
@@ -378,7 +380,7 @@ int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumula
         }
         if (rc == RN_OK && peers_done) *peers_done = true;  // the chained kernel stores to the peers itself
     }
-    if (rc == 1 && g_dense_version >= 3) {
+    if (rc == 1 && dense_version >= 3) {
         switch (m->dense_degree) {
             case 0:
             case 1: rc = launch_v3_deg<1>(m, d_in, wrap, accumulate, num_frames, d_alpha, stream); break;
@@ -396,7 +398,7 @@ int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumula
 // Test / tuning hooks (not in the public header).
 extern "C" void rn_debug_set_dense_config(int version, int unused) {
     (void)unused;
-    rn::g_dense_version = version;
+    rn::g_dense_version.store(version, std::memory_order_relaxed);
 }
 // 0 = whole frame tiles per CTA, 1 = automatic (default), 2 = always balance (frame tile, DOF tile) units
-extern "C" void rn_debug_set_dense_split(int mode) { rn::g_dense_split = mode; }
+extern "C" void rn_debug_set_dense_split(int mode) { rn::g_dense_split.store(mode, std::memory_order_relaxed); }

@@ -340,11 +340,16 @@ __global__ void __launch_bounds__(384, 1)
                     dst[2 * t + 1] = r1;
                     if (t == 0) dst[8] = r8;
                     // fused all-gather: the same row goes to every peer GPU's series over NVLink
-                    for (int p = 0; p < peers.count; p++) {
-                        double* pd = peers.ptr[p] + frame * 9;
-                        pd[2 * t] = r0;
-                        pd[2 * t + 1] = r1;
-                        if (t == 0) pd[8] = r8;
+                    if (peers.count > 0) {
+                        const uint32_t mask = alpha_peer_mask(peers, frame, 1);
+                        const int64_t off = alpha_peer_offset(peers, frame);
+                        for (int p = 0; p < peers.count; p++) {
+                            if (!((mask >> p) & 1u) || !peers.ptr[p]) continue;
+                            double* pd = peers.ptr[p] + off;
+                            pd[2 * t] = r0;
+                            pd[2 * t + 1] = r1;
+                            if (t == 0) pd[8] = r8;
+                        }
                     }
                 }
             }

@@ -206,11 +206,13 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
             // fused all-gather: the previous tile's finished rows (staged in smem, complete since this
             // barrier) go to every peer GPU as one TMA bulk store each (UBLKCP S2G over NVLink)
             const uint32_t src = smem_u32(outbuf + (size_t)((i - 1) & 1) * ROWS * 9);
+            const uint32_t mask = alpha_peer_mask(peers, pending_tile * ROWS, ROWS);
+            const int64_t off = alpha_peer_offset(peers, pending_tile * ROWS);
             for (int p = 0; p < peers.count; p++)
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                                 peers.ptr[p] + pending_tile * (int64_t)(ROWS * 9)),
-                             "r"(src), "r"((uint32_t)(ROWS * 72))
-                             : "memory");
+                if (((mask >> p) & 1u) && peers.ptr[p])
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(peers.ptr[p] + off),
+                                 "r"(src), "r"((uint32_t)(ROWS * 72))
+                                 : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         {
@@ -241,7 +243,10 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async-proxy reads
             } else if (frame < num_frames) {
                 // partial last tile / unaligned peers: plain stores over NVLink
-                for (int p = 0; p < peers.count; p++) peers.ptr[p][frame * 9 + q] = value;
+                const uint32_t mask = alpha_peer_mask(peers, frame, 1);
+                const int64_t off = alpha_peer_offset(peers, frame);
+                for (int p = 0; p < peers.count; p++)
+                    if (((mask >> p) & 1u) && peers.ptr[p]) peers.ptr[p][off + q] = value;
             }
         }
         if (peers_bulk && threadIdx.x == 32) {
@@ -254,18 +259,20 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
         __syncthreads();
         if (threadIdx.x == 32 && pending_tile >= 0) {
             const uint32_t src = smem_u32(outbuf + (size_t)((i - 1) & 1) * ROWS * 9);
+            const uint32_t mask = alpha_peer_mask(peers, pending_tile * ROWS, ROWS);
+            const int64_t off = alpha_peer_offset(peers, pending_tile * ROWS);
             for (int p = 0; p < peers.count; p++)
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                                 peers.ptr[p] + pending_tile * (int64_t)(ROWS * 9)),
-                             "r"(src), "r"((uint32_t)(ROWS * 72))
-                             : "memory");
+                if (((mask >> p) & 1u) && peers.ptr[p])
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(peers.ptr[p] + off),
+                                 "r"(src), "r"((uint32_t)(ROWS * 72))
+                                 : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (threadIdx.x == 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
-static int g_affine_mt = 0;  // 0 = automatic
+static std::atomic<int> g_affine_mt{0};  // 0 = automatic (A/B switch, include/ramannoodle_b200_debug.h)
 
 template <int KP, int MT, int STAGES, bool WRAP>
 static int launch_affine_tma_cfg(const rn_model* m, const double* d_in, int64_t frames, double* d_alpha, Alpha0 a0,
@@ -285,7 +292,8 @@ static int launch_affine_tma_cfg(const rn_model* m, const double* d_in, int64_t 
     // bulk (TMA) stores to the peers need 16-byte aligned destinations
     int peers_bulk = peers.count > 0 ? 1 : 0;
     for (int p = 0; p < peers.count; p++)
-        if (reinterpret_cast<uintptr_t>(peers.ptr[p]) % 16 != 0) peers_bulk = 0;
+        if (peers.ptr[p] && reinterpret_cast<uintptr_t>(peers.ptr[p]) % 16 != 0) peers_bulk = 0;
+    if (peers.log2_period >= 0 && (peers.first_frame * 72) % 16 != 0) peers_bulk = 0;
     kern<<<grid, kAffineWarps * 32, L.bytes, stream>>>(d_in, ref, G, frames, K, L.row_stride, L.stage_doubles, a0,
                                                        d_alpha, peers, peers_bulk);
     RN_LAUNCHED();
@@ -298,7 +306,7 @@ static int launch_affine_tma_kp(const rn_model* m, const double* d_in, int64_t f
                                 cudaStream_t stream, const AlphaPeers& peers) {
     // Measured on B200 (tools/tune_affine.py, 1M frames): LLZO (KP=9) 16-frame tiles, 1 CTA/SM:
     // 6284 GB/s; 8-frame tiles, 2 CTAs/SM: 6200 GB/s.  TiO2 (KP=6): 4855 vs 5127 GB/s.
-    int mt = g_affine_mt;
+    int mt = g_affine_mt.load(std::memory_order_relaxed);
     if (mt == 0) mt = (KP >= 8) ? 2 : 1;
     int rc = 1;
     if (mt == 2) rc = launch_affine_tma_cfg<KP, 2, 2, WRAP>(m, d_in, frames, d_alpha, a0, stream, peers);
@@ -345,7 +353,7 @@ static int launch_affine_generic(const rn_model* m, const double* d_in, int64_t 
     return RN_OK;
 }
 
-static bool g_force_generic_affine = false;
+static std::atomic<bool> g_force_generic_affine{false};
 
 int launch_affine(const rn_model* m, const double* d_in, bool wrap, int64_t num_frames, double* d_alpha,
                   cudaStream_t stream, const AlphaPeers* peers, bool* peers_done) {
@@ -354,12 +362,11 @@ int launch_affine(const rn_model* m, const double* d_in, bool wrap, int64_t num_
     const int K = (int)m->dim;
     const bool aligned = (reinterpret_cast<uintptr_t>(d_in) % 16) == 0 && (K % 2 == 0);
     int64_t tma_frames = 0;
-    if (m->affine_kp > 0 && aligned && !g_force_generic_affine) {
+    if (m->affine_kp > 0 && aligned && !g_force_generic_affine.load(std::memory_order_relaxed)) {
         tma_frames = num_frames;
     }
     int rc = RN_OK;
-    AlphaPeers fused;
-    fused.count = 0;
+    AlphaPeers fused = no_peers();
     if (peers) fused = *peers;
     if (tma_frames > 0) {
         rc = wrap ? launch_affine_tma<true>(m, d_in, tma_frames, d_alpha, a0, stream, fused)
@@ -644,9 +651,13 @@ static int eval_common(const rn_model* model, const double* d_in, bool wrap, int
         if (run_dense) rc = launch_dense(model, d_in, wrap, run_affine, num_frames, d_alpha, s, peers, &peers_done);
     }
     if (rc != RN_OK) return rc;
-    if (peers && !peers_done) {  // kernels without fused peer stores: plain device-to-peer copies
+    if (peers && !peers_done) {
+        // kernels without fused peer stores: plain device-to-peer copies of the whole block (routed mode:
+        // to every rank — rows a rank does not own are simply never read there)
         for (int p = 0; p < peers->count; p++)
-            RN_CUDA(cudaMemcpyAsync(peers->ptr[p], d_alpha, sizeof(double) * 9 * num_frames, cudaMemcpyDeviceToDevice, s));
+            if (peers->ptr[p])
+                RN_CUDA(cudaMemcpyAsync(peers->ptr[p] + alpha_peer_offset(*peers, 0), d_alpha,
+                                        sizeof(double) * 9 * num_frames, cudaMemcpyDeviceToDevice, s));
     }
     return RN_OK;
 }
@@ -654,6 +665,7 @@ static int eval_common(const rn_model* model, const double* d_in, bool wrap, int
 static int make_peers(double* const* d_alpha_outputs, int num_outputs, AlphaPeers* peers) {
     RN_CHECK_ARG(d_alpha_outputs != nullptr && num_outputs >= 1 && num_outputs <= 8,
                  "between 1 and 8 output pointers are required");
+    *peers = no_peers();
     peers->count = num_outputs - 1;
     for (int i = 0; i < num_outputs; i++) RN_CHECK_ARG(d_alpha_outputs[i] != nullptr, "null output pointer");
     for (int i = 1; i < num_outputs; i++) peers->ptr[i - 1] = d_alpha_outputs[i];
@@ -668,6 +680,25 @@ extern "C" int rn_calc_polarizabilities_multi(const rn_model* model, const doubl
     return eval_common(model, d_positions, true, num_frames, d_alpha_outputs[0], stream, &peers);
 }
 
+extern "C" int rn_calc_polarizabilities_routed(const rn_model* model, const double* d_positions, int64_t num_frames,
+                                               double* d_alpha, double* const* peer_series, int world,
+                                               int64_t first_frame, int64_t period, int64_t width, void* stream) {
+    RN_CHECK_ARG(peer_series != nullptr && world >= 1 && world <= 8, "between 1 and 8 ranks");
+    RN_CHECK_ARG(first_frame >= 0, "first_frame must be non-negative");
+    RN_CHECK_ARG(period > 0 && (period & (period - 1)) == 0 && width >= 32 && (width & (width - 1)) == 0 &&
+                     width <= period && period / width <= world,
+                 "period and width must be powers of two with width >= 32 and period / width <= world");
+    AlphaPeers peers = no_peers();
+    peers.count = world;
+    for (int r = 0; r < world; r++) peers.ptr[r] = peer_series[r];
+    peers.log2_period = 0;
+    while (((int64_t)1 << peers.log2_period) < period) peers.log2_period++;
+    peers.log2_width = 0;
+    while (((int64_t)1 << peers.log2_width) < width) peers.log2_width++;
+    peers.first_frame = first_frame;
+    return eval_common(model, d_positions, true, num_frames, d_alpha, stream, &peers);
+}
+
 extern "C" int rn_calc_polarizabilities(const rn_model* model, const double* d_positions, int64_t num_frames,
                                         double* d_alpha, void* stream) {
     return eval_common(model, d_positions, true, num_frames, d_alpha, stream);
@@ -678,12 +709,12 @@ extern "C" int rn_get_polarizability(const rn_model* model, const double* d_cart
     return eval_common(model, d_cart_displacements, false, num_frames, d_alpha, stream);
 }
 
-// Test hook (not in the public header): route the affine term through the generic kernel.
-extern "C" void rn_debug_force_generic_affine(int on) { rn::g_force_generic_affine = on != 0; }
+// Test hook (include/ramannoodle_b200_debug.h): route the affine term through the generic kernel.
+extern "C" void rn_debug_force_generic_affine(int on) { rn::g_force_generic_affine.store(on != 0, std::memory_order_relaxed); }
 // Tuning hook: frames-per-tile multiplier (1 or 2) and pipeline depth of the TMA affine kernel.
 extern "C" void rn_debug_set_affine_config(int mt, int stages) {
     (void)stages;
-    rn::g_affine_mt = mt;
+    rn::g_affine_mt.store(mt, std::memory_order_relaxed);
 }
 
 __global__ void apply_pbc_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t count) {

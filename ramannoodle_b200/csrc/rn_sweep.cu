@@ -299,8 +299,8 @@ static int launch_sweep(int nt, const rn_model* m, const double* d_in, int64_t f
     }
 }
 
-static bool g_sweep_fused = true;
-static int g_sweep_min_run = 3;
+static std::atomic<bool> g_sweep_fused{true};  // A/B switches (include/ramannoodle_b200_debug.h)
+static std::atomic<int> g_sweep_min_run{3};
 
 // models that the fused kernel can take together: purely affine, TMA-eligible, same structure
 static bool sweep_compatible(const rn_model* a, const rn_model* b) {
@@ -420,6 +420,6 @@ extern "C" int rn_calc_polarizabilities_sweep(const rn_model* const* models, int
 }
 
 // test hook: 0 = always evaluate the models one after the other
-extern "C" void rn_debug_set_sweep_fused(int on) { rn::g_sweep_fused = on != 0; }
+extern "C" void rn_debug_set_sweep_fused(int on) { rn::g_sweep_fused.store(on != 0, std::memory_order_relaxed); }
 // test hook: shortest run of models that is fused (2..4; default 3)
-extern "C" void rn_debug_set_sweep_min_run(int run) { rn::g_sweep_min_run = run < 2 ? 2 : (run > 4 ? 4 : run); }
+extern "C" void rn_debug_set_sweep_min_run(int run) { rn::g_sweep_min_run.store(run < 2 ? 2 : (run > 4 ? 4 : run), std::memory_order_relaxed); }

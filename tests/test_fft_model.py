@@ -1,0 +1,59 @@
+"""CPU checks of the schedule the spectrum kernels implement (tests/fft_model.py restates the index
+arithmetic of csrc/rn_fft.cuh and csrc/rn_spectrum.cu in numpy): the in-place DIF transform against
+numpy.fft through its digit-reversal map, the convolution (forward, filter, mirrored inverse), and the
+whole measure — packed weighted signals, chirp-z, rank-level decimation — against the oracle."""
+import numpy as np
+import pytest
+
+import fft_model as fm
+from oracle import numpy_port as ora
+
+
+@pytest.mark.parametrize("log2lh", [12, 13, 14, 15, 16, 18])
+def test_forward_is_a_permuted_fft(log2lh):
+    rng = np.random.default_rng(log2lh)
+    n = 1 << log2lh
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    y = x.copy()
+    fm.forward(y, log2lh)
+    ref = np.fft.fft(x)
+    perm = fm.frequency_of_position(log2lh)
+    assert sorted(perm.tolist()) == list(range(n))
+    assert np.abs(y - ref[perm]).max() / np.abs(ref).max() < 1e-13
+
+
+def test_two_level_plan_forward():
+    log2lh = 23  # 2^11 rows above the tiles -> levels of 2^6 and 2^5
+    assert fm.plan_levels(log2lh) == [6, 5]
+    rng = np.random.default_rng(0)
+    n = 1 << log2lh
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    y = x.copy()
+    fm.forward(y, log2lh)
+    ref = np.fft.fft(x)
+    assert np.abs(y - ref[fm.frequency_of_position(log2lh)]).max() / np.abs(ref).max() < 1e-13
+
+
+@pytest.mark.parametrize("log2lh", [12, 14, 16])
+def test_convolution(log2lh):
+    rng = np.random.default_rng(100 + log2lh)
+    n = 1 << log2lh
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    h = rng.normal(size=n) + 1j * rng.normal(size=n)
+    hperm = h.copy()
+    fm.forward(hperm, log2lh)
+    y = x.copy()
+    fm.convolve(y, hperm, log2lh)
+    ref = np.fft.ifft(np.fft.fft(x) * np.fft.fft(h)) * n
+    assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-13
+
+
+@pytest.mark.parametrize("frames,world", [(41, 1), (41, 8), (1000, 2), (4097, 4), (5000, 1), (5000, 8), (20_001, 2)])
+def test_measure_model_matches_oracle(frames, world):
+    rng = np.random.default_rng(frames)
+    steps = np.arange(frames)[:, None, None]
+    alpha = (6.0 * np.eye(3)[None] + 0.05 * np.sin(0.013 * steps + rng.uniform(0, 6, (1, 3, 3)))
+             + 0.01 * rng.normal(size=(frames, 3, 3)))
+    _, ref = ora.md_measure(alpha, 1.0)
+    got = fm.md_intensities(alpha, world)
+    assert np.abs(got / ref - 1).max() < 1e-11

@@ -148,179 +148,140 @@ def test_spectrum_error_behaviour():
         rb.convolve_spectrum(np.array([1.0, 2.0, 3.0]), np.array([0.0, 3.0]), "gaussian", 5)
 
 
-@pytest.mark.parametrize("log2l", [3, 4, 5, 6, 7, 9, 10, 12, 13, 14, 16, 17, 20, 21, 22, 23, 24])
-def test_tiled_fft_against_torch(log2l):
-    """The hand-written tiled Stockham FFT (1, 2 and 3 global passes; first sub-pass radix 2, 4
-    and 8) against torch.fft (cuFFT) in both directions."""
-    import ctypes
+def _random_complex(length, seed):
+    gen = torch.Generator("cuda:0").manual_seed(seed)
+    return torch.randn(length, 2, dtype=torch.float64, device="cuda:0", generator=gen)
 
-    from ramannoodle_b200 import _lib
+
+def _plan_for_length(log2l):
     from ramannoodle_b200.spectrum import _get_plan
 
-    length = 1 << log2l
-    frames = (length >> 1) + 1  # M = L/2 -> Bluestein length L
-    plan = _get_plan(frames, 0)
-    gen = torch.Generator("cuda:0").manual_seed(log2l)
-    x = torch.randn(length, 2, dtype=torch.float64, device="cuda:0", generator=gen)
+    frames = ((1 << log2l) >> 1) + 1  # M = L/2 -> chirp-z length L (L >= 4096 always)
+    return _get_plan(frames, 0), frames - 1
+
+
+@pytest.mark.parametrize("log2l", [12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24])
+def test_fft_forward_against_torch(log2l):
+    """The in-place DIF forward transform (no level, one level with last radix 2 / 4 / 8, two levels)
+    against torch.fft (cuFFT), through the digit-reversal map of tests/fft_model.py."""
+    import ctypes
+
+    import fft_model
+    from ramannoodle_b200 import _lib
+
+    plan, _ = _plan_for_length(log2l)
+    info = (ctypes.c_int64 * 8)()
+    assert _lib.lib().rn_spectrum_plan_info(plan.handle, info) == 0
+    assert info[0] == log2l and info[1] == 1 and info[2] == log2l
+    levels = fft_model.plan_levels(log2l)
+    assert info[3] == len(levels) and [info[4], info[5]][: len(levels)] == levels
+    x = _random_complex(1 << log2l, log2l)
     out = torch.empty_like(x)
-    lib = _lib.lib()
-    lib.rn_debug_fft.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
-    lib.rn_debug_fft.restype = ctypes.c_int
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    xc = torch.view_as_complex(x)
-    for sign, ref in ((-1, torch.fft.fft(xc)), (1, torch.fft.ifft(xc) * length)):
-        assert lib.rn_debug_fft(plan.handle, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), sign,
-                                stream) == 0
-        got = torch.view_as_complex(out)
-        err = float((got - ref).abs().max() / ref.abs().max())
-        assert err < 1e-13, f"L=2^{log2l} sign={sign}: {err}"
+    assert _lib.lib().rn_debug_fft_forward(plan.handle, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                           stream) == 0
+    ref = torch.fft.fft(torch.view_as_complex(x))
+    perm = torch.from_numpy(fft_model.frequency_of_position(log2l)).to("cuda:0")
+    got = torch.view_as_complex(out)
+    err = float((got - ref[perm]).abs().max() / ref.abs().max())
+    assert err < 1e-13, f"L=2^{log2l}: {err}"
 
 
-@pytest.mark.parametrize("frames", [41, 1000, 4097, 50_001])
-def test_sharded_parts_sum_to_measure(frames):
-    """The three packed transforms of the sharded measure (rn_md_spectrum_part) add up to
-    MDRamanSpectrum.measure (oracle parity for the multi-GPU spectrum path on one GPU)."""
+@pytest.mark.parametrize("log2l", [12, 13, 15, 16, 18, 21, 22, 23])
+def test_fft_convolve_against_torch(log2l):
+    """Forward transform, filter multiply and mirrored inverse (the whole convolution core) against
+    ifft(fft(x) fft(h)) with the chirp filter h built in torch."""
     import ctypes
 
     from ramannoodle_b200 import _lib
-    from ramannoodle_b200.distributed import spectrum_parts
-    from ramannoodle_b200.spectrum import _get_plan
 
-    rng = np.random.default_rng(frames)
-    steps = np.arange(frames)[:, None, None]
-    alpha = (6.0 * np.eye(3)[None] + 0.05 * np.sin(0.011 * steps + rng.uniform(0, 6, (1, 3, 3)))
-             + 0.01 * rng.normal(size=(frames, 3, 3)))
-    ref_wn, ref_inten = ora.md_measure(alpha, 2.0, laser_correction=True, laser_wavelength=532,
-                                       bose_einstein_correction=True, temperature=250)
+    plan, m_len = _plan_for_length(log2l)
+    length = 1 << log2l
+    x = _random_complex(length, 100 + log2l)
+    out = torch.empty_like(x)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert _lib.lib().rn_debug_fft_convolve(plan.handle, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                            stream) == 0
+    idx = torch.arange(length, device="cuda:0", dtype=torch.int64)
+    m = torch.where(idx < m_len, idx, torch.where(length - idx < m_len, length - idx, torch.full_like(idx, -1)))
+    phase = ((m * m) % (2 * m_len)).to(torch.float64) / m_len
+    h = torch.where(m >= 0, torch.exp(1j * torch.pi * phase), torch.zeros((), dtype=torch.complex128, device="cuda:0"))
+    ref = torch.fft.ifft(torch.fft.fft(torch.view_as_complex(x)) * torch.fft.fft(h)) * length
+    err = float((torch.view_as_complex(out) - ref).abs().max() / ref.abs().max())
+    assert err < 1e-12, f"L=2^{log2l}: {err}"
+
+
+def _emulated_shared_measure(alpha, timestep, world, **corrections):
+    """The multi-GPU measure (rn_spectrum_dist_*: one transform shared by `world` ranks) with every
+    rank emulated on cuda:0 — the same kernels and buffers, peers being local pointers."""
+    import ctypes
+
+    from ramannoodle_b200 import _lib
+
+    lib = _lib.lib()
+    frames = alpha.shape[0]
     d_alpha = to_cuda(alpha)
-    lib = _lib.lib()
-    plan = _get_plan(frames, 0)
-    points = int(lib.rn_spectrum_num_points(frames))
-    total = torch.zeros(points, dtype=torch.float64, device="cuda:0")
-    part = torch.empty_like(total)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    assert sorted(spectrum_parts(2, 0) + spectrum_parts(2, 1)) == [0, 1, 2]
-    assert [spectrum_parts(8, r) for r in range(4)] == [[0], [1], [2], []]
-    for index in range(3):
-        assert lib.rn_md_spectrum_part(plan.handle, ctypes.c_void_p(d_alpha.data_ptr()), index,
-                                       ctypes.c_void_p(part.data_ptr()), stream) == 0
-        total += part
-    wn = torch.empty_like(total)
-    inten = torch.empty_like(total)
-    assert lib.rn_md_spectrum_finish(frames, ctypes.c_void_p(total.data_ptr()), 2.0, 1, 532.0, 1, 250.0,
-                                     ctypes.c_void_p(wn.data_ptr()), ctypes.c_void_p(inten.data_ptr()), stream) == 0
-    assert np.array_equal(wn.cpu().numpy(), ref_wn)
-    assert pointwise_rel_err(inten.cpu().numpy(), ref_inten) <= INTENSITY_RTOL
+    plans = []
+    for rank in range(world):
+        handle = ctypes.c_void_p()
+        assert lib.rn_spectrum_plan_create_dist(frames, 0, world, rank, ctypes.byref(handle)) == 0
+        plans.append(handle)
+    try:
+        sizes = [ctypes.c_int64() for _ in range(3)]
+        assert lib.rn_spectrum_dist_sizes(plans[0], *[ctypes.byref(v) for v in sizes]) == 0
+        work = [torch.full((sizes[0].value // 8,), float("nan"), dtype=torch.float64, device="cuda:0") for _ in range(world)]
+        recv = [torch.full((sizes[1].value // 8,), float("nan"), dtype=torch.float64, device="cuda:0") for _ in range(world)]
+        power = [torch.full((sizes[2].value // 8,), float("nan"), dtype=torch.float64, device="cuda:0") for _ in range(world)]
+        info = (ctypes.c_int64 * 8)()
+        assert lib.rn_spectrum_plan_info(plans[0], info) == 0
+        group = int(info[1])
+
+        def table(tensors):
+            return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+        for rank in range(world):
+            assert lib.rn_spectrum_dist_pack(plans[rank], ctypes.c_void_p(d_alpha.data_ptr()), table(work[:group]), stream) == 0
+        for rank in range(world):
+            assert lib.rn_spectrum_dist_transform(plans[rank], ctypes.c_void_p(work[rank].data_ptr()), table(recv[:group]),
+                                                  stream) == 0
+        for rank in range(world):
+            assert lib.rn_spectrum_dist_final(plans[rank], ctypes.c_void_p(recv[rank].data_ptr()), table(power), world,
+                                              stream) == 0
+        points = int(lib.rn_spectrum_num_points(frames))
+        results = []
+        for rank in range(world):
+            wn = torch.empty(points, dtype=torch.float64, device="cuda:0")
+            inten = torch.empty(points, dtype=torch.float64, device="cuda:0")
+            assert lib.rn_spectrum_dist_combine(
+                plans[rank], ctypes.c_void_p(power[rank].data_ptr()), float(timestep),
+                1 if "laser_wavelength" in corrections else 0, float(corrections.get("laser_wavelength", 0.0)),
+                1 if "temperature" in corrections else 0, float(corrections.get("temperature", 0.0)),
+                ctypes.c_void_p(wn.data_ptr()), ctypes.c_void_p(inten.data_ptr()), stream) == 0
+            results.append((wn.cpu().numpy(), inten.cpu().numpy()))
+        return results
+    finally:
+        for handle in plans:
+            lib.rn_spectrum_plan_destroy(handle)
 
 
-@pytest.mark.parametrize("frames", [41, 1000, 4097, 50_001, 300_000])
-def test_split_transforms_sum_to_measure(frames):
-    """The two-rank split of every packed transform (rn_md_spectrum_half + rn_md_spectrum_half_combine:
-    residues 0/1, each finishing half of the bins) emulated on one GPU: the six partial spectra add up
-    to MDRamanSpectrum.measure (oracle, 1e-8) and to rn_md_spectrum_part's (1e-12)."""
-    import ctypes
-
-    from ramannoodle_b200 import _lib
-    from ramannoodle_b200.distributed import spectrum_half_units
-    from ramannoodle_b200.spectrum import _get_plan
-
-    rng = np.random.default_rng(frames + 1)
+@pytest.mark.parametrize("frames,world", [(41, 2), (41, 8), (1000, 4), (4097, 2), (9000, 8), (50_001, 2), (50_001, 3),
+                                          (50_001, 4), (50_001, 8), (300_000, 8), (300_000, 6)])
+def test_shared_transform_matches_measure(frames, world):
+    """One chirp-z transform decimated over 2 / 4 / 8 ranks (3 and 6 ranks: the largest power of two
+    transforms, the rest only receive) reproduces MDRamanSpectrum.measure on every rank."""
+    rng = np.random.default_rng(frames + world)
     steps = np.arange(frames)[:, None, None]
     alpha = (6.0 * np.eye(3)[None] + 0.05 * np.sin(0.013 * steps + rng.uniform(0, 6, (1, 3, 3)))
              + 0.01 * rng.normal(size=(frames, 3, 3)))
-    ref_wn, ref_inten = ora.md_measure(alpha, 1.5, laser_correction=True, laser_wavelength=532)
-    d_alpha = to_cuda(alpha)
-    lib = _lib.lib()
-    plan = _get_plan(frames, 0)
-    points = int(lib.rn_spectrum_num_points(frames))
-    half = int(lib.rn_spectrum_half_length(plan.handle))
-    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
-
-    # schedules: every (part, residue) unit is owned exactly once and partners are mutual
-    for world in (2, 6, 8):
-        owned = []
-        for rank in range(world):
-            units, partner = spectrum_half_units(world, rank)
-            owned += units
-            if units:
-                assert spectrum_half_units(world, partner)[1] == rank
-                assert [(p, 1 - r) for p, r in units] == spectrum_half_units(world, partner)[0]
-        assert sorted(owned) == [(p, r) for p in range(3) for r in range(2)]
-    assert spectrum_half_units(4, 1) is None and spectrum_half_units(1, 0) is None
-
-    total = torch.zeros(points, dtype=torch.float64, device="cuda:0")
-    by_part = torch.zeros(points, dtype=torch.float64, device="cuda:0")
-    for part in range(3):
-        z = torch.full((2, half, 2), float("nan"), dtype=torch.float64, device="cuda:0")
-        for residue in range(2):
-            assert lib.rn_md_spectrum_half(plan.handle, ptr(d_alpha), part, residue, ptr(z[residue]), residue, stream) == 0
-        piece = torch.full((points,), float("nan"), dtype=torch.float64, device="cuda:0")
-        assert lib.rn_md_spectrum_half_combine(plan.handle, part, 0, ptr(z[0]), ptr(z[1]), ptr(piece), 0, stream) == 0
-        assert lib.rn_md_spectrum_half_combine(plan.handle, part, 1, ptr(z[0]), ptr(z[1]), ptr(piece), 1, stream) == 0
-        assert lib.rn_md_spectrum_part(plan.handle, ptr(d_alpha), part, ptr(by_part), stream) == 0
-        assert rel_err(piece.cpu().numpy(), by_part.cpu().numpy()) <= 1e-12
-        total += piece
-    wn = torch.empty_like(total)
-    inten = torch.empty_like(total)
-    assert lib.rn_md_spectrum_finish(frames, ptr(total), 1.5, 1, 532.0, 0, 0.0, ptr(wn), ptr(inten), stream) == 0
-    assert np.array_equal(wn.cpu().numpy(), ref_wn)
-    assert pointwise_rel_err(inten.cpu().numpy(), ref_inten) <= INTENSITY_RTOL
-
-
-@pytest.mark.parametrize("frames", [41, 4097, 120_001])
-def test_sharded_energy_constant(frames):
-    """Energy mode 1 (multi-GPU measure): parts and half transforms without the series energies plus
-    the constants of three frame shards (rn_series_energy_constant) equal the default computation."""
-    import ctypes
-
-    from ramannoodle_b200 import _lib
-    from ramannoodle_b200.distributed import shard_bounds
-    from ramannoodle_b200.spectrum import _get_plan
-
-    rng = np.random.default_rng(frames + 7)
-    alpha = 6.0 * np.eye(3)[None] + 0.02 * rng.normal(size=(frames, 3, 3)).cumsum(axis=0) / np.sqrt(frames)
-    d_alpha = to_cuda(alpha)
-    lib = _lib.lib()
-    plan = _get_plan(frames, 0)
-    points = int(lib.rn_spectrum_num_points(frames))
-    half = int(lib.rn_spectrum_half_length(plan.handle))
-    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
-
-    def parts_total():
-        total = torch.zeros(points, dtype=torch.float64, device="cuda:0")
-        piece = torch.empty_like(total)
-        for part in range(3):
-            assert lib.rn_md_spectrum_part(plan.handle, ptr(d_alpha), part, ptr(piece), stream) == 0
-            total += piece
-        return total
-
-    def halves_total():
-        total = torch.zeros(points, dtype=torch.float64, device="cuda:0")
-        z = torch.empty((2, half, 2), dtype=torch.float64, device="cuda:0")
-        for part in range(3):
-            for residue in range(2):
-                assert lib.rn_md_spectrum_half(plan.handle, ptr(d_alpha), part, residue, ptr(z[residue]),
-                                               0 if (part == 0 and residue == 0) else 1, stream) == 0
-            for residue in range(2):
-                assert lib.rn_md_spectrum_half_combine(plan.handle, part, residue, ptr(z[0]), ptr(z[1]), ptr(total), 1,
-                                                       stream) == 0
-        return total
-
-    want = parts_total()
-    assert lib.rn_spectrum_set_energy_mode(plan.handle, 1) == 0
-    try:
-        bare_parts = parts_total()
-        bare_halves = halves_total()
-        constant = torch.zeros(3, dtype=torch.float64, device="cuda:0")
-        for rank in range(3):
-            begin, end = shard_bounds(frames - 1, 3, rank)
-            assert lib.rn_series_energy_constant(plan.handle, ptr(d_alpha), begin, end, ptr(constant[rank:]), stream) == 0
-    finally:
-        assert lib.rn_spectrum_set_energy_mode(plan.handle, 0) == 0
-    shift = constant.sum()
-    assert float(shift) > 0
-    assert rel_err((bare_parts + shift).cpu().numpy(), want.cpu().numpy()) <= 1e-12
-    assert rel_err((bare_halves + shift).cpu().numpy(), want.cpu().numpy()) <= 1e-12
-    assert rel_err(parts_total().cpu().numpy(), want.cpu().numpy()) == 0.0  # mode restored
+    ref_wn, ref_inten = ora.md_measure(alpha, 1.5, laser_correction=True, laser_wavelength=532,
+                                       bose_einstein_correction=True, temperature=250)
+    results = _emulated_shared_measure(alpha, 1.5, world, laser_wavelength=532, temperature=250)
+    single = rb.MDRamanSpectrum(alpha, 1.5).measure(laser_correction=True, laser_wavelength=532,
+                                                    bose_einstein_correction=True, temperature=250)[1]
+    for wn, inten in results:
+        assert np.array_equal(wn, ref_wn)
+        assert pointwise_rel_err(inten, ref_inten) <= INTENSITY_RTOL
+        assert pointwise_rel_err(inten, single) <= 1e-11
+    for wn, inten in results[1:]:
+        assert np.array_equal(inten, results[0][1])  # every rank holds the same bits

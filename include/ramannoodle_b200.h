@@ -110,7 +110,25 @@ int rn_calc_polarizabilities_multi(const rn_model* model, const double* d_positi
                                    int num_outputs, void* stream);
 int rn_calc_polarizabilities_host_multi(const rn_model* model, const double* h_positions,
                                         int64_t num_frames, double* const* d_alpha_outputs,
-                                        int num_outputs, int64_t chunk_frames);
+                                        int num_outputs, int64_t chunk_frames, void* stream);
+
+/* Routed form for the shared multi-GPU spectrum (rn_spectrum_dist_*): the rows are stored to
+ * d_alpha (this rank's block inside its own full (S,3,3) series buffer, i.e. buffer + first_frame*9)
+ * and, by the kernels themselves over NVLink, to the series buffers of the ranks whose spectrum
+ * stage consumes them: row n = first_frame + local row goes to owner(n) and owner(n-1) with
+ * owner(n) = (n mod period) / width  (rn_spectrum_dist_route).  peer_series[r] is the BASE of rank r's
+ * full series buffer (peer-mapped); NULL for this rank itself and for ranks that own nothing.
+ * The host form streams h_positions like rn_calc_polarizabilities_host; its private streams start
+ * after the work already enqueued on `stream` (e.g. a cross-rank barrier) and it returns when done. */
+int rn_calc_polarizabilities_routed(const rn_model* model, const double* d_positions,
+                                    int64_t num_frames, double* d_alpha, double* const* peer_series,
+                                    int world, int64_t first_frame, int64_t period, int64_t width,
+                                    void* stream);
+int rn_calc_polarizabilities_host_routed(const rn_model* model, const double* h_positions,
+                                         int64_t num_frames, double* d_alpha,
+                                         double* const* peer_series, int world, int64_t first_frame,
+                                         int64_t period, int64_t width, int64_t chunk_frames,
+                                         void* stream);
 
 /* Mask sweeps: num_models models of ONE structure — in practice the
  * get_masked_model copies of a model (pmodel/_interpolation.py:697-708; ARTModel.get_dof_indexes,

@@ -39,7 +39,15 @@ PROTOTYPES = {
     "rn_calc_polarizabilities_multi": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "rn_calc_polarizabilities_host_multi": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
-                                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int64]),
+                                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                           ctypes.c_void_p]),
+    "rn_calc_polarizabilities_routed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                       ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "rn_calc_polarizabilities_host_routed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                            ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                            ctypes.c_int64, ctypes.c_void_p]),
     "rn_apply_pbc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
     "rn_spectrum_plan_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "rn_spectrum_plan_destroy": (ctypes.c_int, [ctypes.c_void_p]),

@@ -147,6 +147,11 @@ int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumula
 int launch_dense_v1(const rn_model* m, const double* d_in, bool wrap, bool accumulate, int64_t num_frames,
                     double* d_alpha, cudaStream_t stream);
 int launch_fill_alpha0(const rn_model* m, int64_t num_frames, double* d_alpha, cudaStream_t stream);
+// rn_polarizability.cu: calc_polarizabilities of `num_frames` device-resident frames with extra destinations
+int eval_with_peers(const rn_model* model, const double* d_positions, int64_t num_frames, double* d_alpha,
+                    cudaStream_t stream, const AlphaPeers& peers);
+int make_routed_peers(double* const* peer_series, int world, int64_t first_frame, int64_t period, int64_t width,
+                      AlphaPeers* peers);
 // rn_dense_sweep.cu: spline part of 2..4 masked copies of one model with a shared projection
 bool dense_sweep_eligible(const rn_model* m);
 bool dense_sweep_compatible(const rn_model* a, const rn_model* b);

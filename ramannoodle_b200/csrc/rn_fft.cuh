@@ -193,14 +193,16 @@ __device__ __forceinline__ void store_out(const OutSpec& out, double2* plain, in
 // splits blocks of Ns = RADIX * sp / B points.  SGN < 0: DIF forward (twiddle W_Ns^{i k} after the
 // butterfly); SGN > 0: DIT inverse, the mirror (conjugate twiddle before the butterfly).
 // rd(pos, slot) / wr(pos, slot, value) move elements; slot = m * RADIX + q numbers the thread's 16 elements.
-template <int SGN, int RADIX, class Rd, class Wr>
+template <int SGN, int RADIX, bool LEAN, class Rd, class Wr>
 __device__ __forceinline__ void fft_stage(int log2sp, int log2b, const double2* __restrict__ wsub, Rd rd, Wr wr) {
     constexpr int NB = kPerThread / RADIX;
     constexpr int LR = Log2<RADIX>::value;
     const int sp = 1 << log2sp;
     const int log2ns = log2sp - log2b + LR;
     const bool has_tw = log2sp > log2b;
-#pragma unroll
+    // LEAN: one butterfly in flight per thread (fewer registers, three CTAs per SM); otherwise the
+    // thread's butterflies are unrolled and interleaved (two CTAs per SM)
+#pragma unroll(LEAN ? 1 : NB)
     for (int m = 0; m < NB; m++) {
         const int u = (int)threadIdx.x + m * kNT;
         const int lo = u & (sp - 1);
@@ -233,8 +235,8 @@ struct TileParams {
     Twiddles tw;
 };
 
-template <bool FWD_ONLY>
-__global__ void __launch_bounds__(kNT, 2) tile_kernel(const __grid_constant__ TileParams P) {
+template <bool FWD_ONLY, bool LEAN>
+__global__ void __launch_bounds__(kNT, LEAN ? 3 : 2) tile_kernel(const __grid_constant__ TileParams P) {
     extern __shared__ __align__(16) unsigned char fft_smem[];
     double2* S = reinterpret_cast<double2*>(fft_smem);
     const int seq = blockIdx.x / P.tiles_per_seq;
@@ -249,14 +251,14 @@ __global__ void __launch_bounds__(kNT, 2) tile_kernel(const __grid_constant__ Ti
         return (tile_base + pos < P.limit) ? base[pos] : make_double2(0.0, 0.0);
     };
 
-    fft_stage<-1, 8>(9, 0, wsub, rd_g, wr_s);
+    fft_stage<-1, 8, LEAN>(9, 0, wsub, rd_g, wr_s);
     __syncthreads();
-    fft_stage<-1, 8>(6, 0, wsub, rd_s, wr_s);
+    fft_stage<-1, 8, LEAN>(6, 0, wsub, rd_s, wr_s);
     __syncthreads();
-    fft_stage<-1, 8>(3, 0, wsub, rd_s, wr_s);
+    fft_stage<-1, 8, LEAN>(3, 0, wsub, rd_s, wr_s);
     __syncthreads();
     // last forward stage, filter multiply and first inverse stage on the same eight registers
-#pragma unroll
+#pragma unroll(LEAN ? 1 : kPerThread / 8)
     for (int m = 0; m < kPerThread / 8; m++) {
         const int pos0 = ((int)threadIdx.x + m * kNT) << 3;
         double2 h[8];
@@ -281,12 +283,12 @@ __global__ void __launch_bounds__(kNT, 2) tile_kernel(const __grid_constant__ Ti
     }
     if (FWD_ONLY) return;
     __syncthreads();
-    fft_stage<+1, 8>(3, 0, wsub, rd_s, wr_s);
+    fft_stage<+1, 8, LEAN>(3, 0, wsub, rd_s, wr_s);
     __syncthreads();
-    fft_stage<+1, 8>(6, 0, wsub, rd_s, wr_s);
+    fft_stage<+1, 8, LEAN>(6, 0, wsub, rd_s, wr_s);
     __syncthreads();
     auto wr_g = [&](int pos, int, double2 v) { store_out(P.out, base + pos, seq, tile_base + pos, v); };
-    fft_stage<+1, 8>(9, 0, wsub, rd_s, wr_g);
+    fft_stage<+1, 8, LEAN>(9, 0, wsub, rd_s, wr_g);
 }
 
 // ---- level kernel: strided radix-R pass (R = 2^log2r <= 1024) over sub-arrays of length Lsub ------
@@ -332,14 +334,14 @@ struct LevelCtx {
 // the stage that touches global memory with the level twiddle: forward = last stage (smem or global in,
 // global out), inverse = first stage (global in, smem or global out).  RADIX-point butterflies over rows
 // rowbase + q at column col; k = krest + q * (R / RADIX).
-template <int SGN, int RADIX, bool SMEM_SIDE>
+template <int SGN, int RADIX, bool SMEM_SIDE, bool LEAN>
 __device__ __forceinline__ void level_twiddle_stage(const LevelCtx<SGN>& C) {
     constexpr int NB = kPerThread / RADIX;
     constexpr int LR = Log2<RADIX>::value;
     const LevelParams& P = C.P;
     const int B = 1 << C.log2b;
     const int groups = (P.log2r - LR) / 3;  // radix-8 digits above this stage's digit
-#pragma unroll
+#pragma unroll(LEAN ? 1 : (RADIX == 8 ? NB : 2))
     for (int m = 0; m < NB; m++) {
         const int u = (int)threadIdx.x + m * kNT;
         const int col = u & (B - 1);
@@ -394,8 +396,8 @@ __device__ __forceinline__ void level_twiddle_stage(const LevelCtx<SGN>& C) {
     }
 }
 
-template <int SGN>
-__global__ void __launch_bounds__(kNT, 2) level_kernel(const __grid_constant__ LevelParams P) {
+template <int SGN, bool LEAN>
+__global__ void __launch_bounds__(kNT, LEAN ? 3 : 2) level_kernel(const __grid_constant__ LevelParams P) {
     extern __shared__ __align__(16) unsigned char fft_smem[];
     double2* S = reinterpret_cast<double2*>(fft_smem);
     const int log2b = kLog2E - P.log2r;
@@ -417,9 +419,9 @@ __global__ void __launch_bounds__(kNT, 2) level_kernel(const __grid_constant__ L
     auto goff = [&](int pos) { return ((int64_t)(pos >> log2b) << log2s) + (pos & (B - 1)); };
 
     if (a8 + (r1 ? 1 : 0) == 1) {  // a single stage: global -> global
-        if (r1 == 1) level_twiddle_stage<SGN, 2, false>(C);
-        else if (r1 == 2) level_twiddle_stage<SGN, 4, false>(C);
-        else level_twiddle_stage<SGN, 8, false>(C);
+        if (r1 == 1) level_twiddle_stage<SGN, 2, false, LEAN>(C);
+        else if (r1 == 2) level_twiddle_stage<SGN, 4, false, LEAN>(C);
+        else level_twiddle_stage<SGN, 8, false, LEAN>(C);
         return;
     }
     if constexpr (SGN < 0) {
@@ -429,26 +431,26 @@ __global__ void __launch_bounds__(kNT, 2) level_kernel(const __grid_constant__ L
             return (elem_base + off < P.limit) ? base[off] : make_double2(0.0, 0.0);
         };
         int log2sp = kLog2E - 3;
-        fft_stage<-1, 8>(log2sp, log2b, wsub, rd_g, wr_s);
+        fft_stage<-1, 8, LEAN>(log2sp, log2b, wsub, rd_g, wr_s);
         __syncthreads();
         const int mid = (r1 ? a8 : a8 - 1) - 1;  // radix-8 stages strictly between the first and the last
         for (int i = 0; i < mid; i++) {
             log2sp -= 3;
-            fft_stage<-1, 8>(log2sp, log2b, wsub, rd_s, wr_s);
+            fft_stage<-1, 8, LEAN>(log2sp, log2b, wsub, rd_s, wr_s);
             __syncthreads();
         }
-        if (r1 == 1) level_twiddle_stage<-1, 2, true>(C);
-        else if (r1 == 2) level_twiddle_stage<-1, 4, true>(C);
-        else level_twiddle_stage<-1, 8, true>(C);
+        if (r1 == 1) level_twiddle_stage<-1, 2, true, LEAN>(C);
+        else if (r1 == 2) level_twiddle_stage<-1, 4, true, LEAN>(C);
+        else level_twiddle_stage<-1, 8, true, LEAN>(C);
     } else {
-        if (r1 == 1) level_twiddle_stage<+1, 2, true>(C);
-        else if (r1 == 2) level_twiddle_stage<+1, 4, true>(C);
-        else level_twiddle_stage<+1, 8, true>(C);
+        if (r1 == 1) level_twiddle_stage<+1, 2, true, LEAN>(C);
+        else if (r1 == 2) level_twiddle_stage<+1, 4, true, LEAN>(C);
+        else level_twiddle_stage<+1, 8, true, LEAN>(C);
         __syncthreads();
         const int mid = (r1 ? a8 : a8 - 1) - 1;
         int log2sp = kLog2E - 3 * (mid + 1);
         for (int i = 0; i < mid; i++) {
-            fft_stage<+1, 8>(log2sp, log2b, wsub, rd_s, wr_s);
+            fft_stage<+1, 8, LEAN>(log2sp, log2b, wsub, rd_s, wr_s);
             __syncthreads();
             log2sp += 3;
         }
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(kNT, 2) level_kernel(const __grid_constant__ L
             const int64_t off = goff(pos);
             store_out(P.out, base + off, seq, elem_base + off, v);
         };
-        fft_stage<+1, 8>(kLog2E - 3, log2b, wsub, rd_s, wr_g);
+        fft_stage<+1, 8, LEAN>(kLog2E - 3, log2b, wsub, rd_s, wr_g);
     }
 }
 

@@ -680,22 +680,35 @@ extern "C" int rn_calc_polarizabilities_multi(const rn_model* model, const doubl
     return eval_common(model, d_positions, true, num_frames, d_alpha_outputs[0], stream, &peers);
 }
 
-extern "C" int rn_calc_polarizabilities_routed(const rn_model* model, const double* d_positions, int64_t num_frames,
-                                               double* d_alpha, double* const* peer_series, int world,
-                                               int64_t first_frame, int64_t period, int64_t width, void* stream) {
+int rn::make_routed_peers(double* const* peer_series, int world, int64_t first_frame, int64_t period, int64_t width,
+                          AlphaPeers* peers) {
     RN_CHECK_ARG(peer_series != nullptr && world >= 1 && world <= 8, "between 1 and 8 ranks");
     RN_CHECK_ARG(first_frame >= 0, "first_frame must be non-negative");
     RN_CHECK_ARG(period > 0 && (period & (period - 1)) == 0 && width >= 32 && (width & (width - 1)) == 0 &&
                      width <= period && period / width <= world,
                  "period and width must be powers of two with width >= 32 and period / width <= world");
-    AlphaPeers peers = no_peers();
-    peers.count = world;
-    for (int r = 0; r < world; r++) peers.ptr[r] = peer_series[r];
-    peers.log2_period = 0;
-    while (((int64_t)1 << peers.log2_period) < period) peers.log2_period++;
-    peers.log2_width = 0;
-    while (((int64_t)1 << peers.log2_width) < width) peers.log2_width++;
-    peers.first_frame = first_frame;
+    *peers = no_peers();
+    peers->count = world;
+    for (int r = 0; r < world; r++) peers->ptr[r] = peer_series[r];
+    peers->log2_period = 0;
+    while (((int64_t)1 << peers->log2_period) < period) peers->log2_period++;
+    peers->log2_width = 0;
+    while (((int64_t)1 << peers->log2_width) < width) peers->log2_width++;
+    peers->first_frame = first_frame;
+    return RN_OK;
+}
+
+int rn::eval_with_peers(const rn_model* model, const double* d_positions, int64_t num_frames, double* d_alpha,
+                        cudaStream_t stream, const AlphaPeers& peers) {
+    return eval_common(model, d_positions, true, num_frames, d_alpha, stream, &peers);
+}
+
+extern "C" int rn_calc_polarizabilities_routed(const rn_model* model, const double* d_positions, int64_t num_frames,
+                                               double* d_alpha, double* const* peer_series, int world,
+                                               int64_t first_frame, int64_t period, int64_t width, void* stream) {
+    AlphaPeers peers;
+    int rc = make_routed_peers(peer_series, world, first_frame, period, width, &peers);
+    if (rc != RN_OK) return rc;
     return eval_common(model, d_positions, true, num_frames, d_alpha, stream, &peers);
 }
 

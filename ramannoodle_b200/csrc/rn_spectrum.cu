@@ -333,16 +333,27 @@ static int grid_for(int64_t n, int sms) {
 static int ensure_smem_attr(int device) {
     static std::atomic<bool> done[64];  // the attribute is per function and per device
     if (device >= 0 && device < 64 && done[device].load(std::memory_order_acquire)) return RN_OK;
-    RN_CUDA(cudaFuncSetAttribute(fft::tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)fft::kTileSmemBytes));
-    RN_CUDA(cudaFuncSetAttribute(fft::tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)fft::kTileSmemBytes));
-    RN_CUDA(cudaFuncSetAttribute(fft::level_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)fft::kTileSmemBytes));
-    RN_CUDA(cudaFuncSetAttribute(fft::level_kernel<+1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)fft::kTileSmemBytes));
+#define RN_FFT_SMEM(kern) \
+    RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft::kTileSmemBytes))
+    RN_FFT_SMEM((fft::tile_kernel<false, false>));
+    RN_FFT_SMEM((fft::tile_kernel<false, true>));
+    RN_FFT_SMEM((fft::tile_kernel<true, false>));
+    RN_FFT_SMEM((fft::level_kernel<-1, false>));
+    RN_FFT_SMEM((fft::level_kernel<-1, true>));
+    RN_FFT_SMEM((fft::level_kernel<+1, false>));
+    RN_FFT_SMEM((fft::level_kernel<+1, true>));
+#undef RN_FFT_SMEM
     if (device >= 0 && device < 64) done[device].store(true, std::memory_order_release);
     return RN_OK;
+}
+
+// kernel variant: bit 0 = lean level kernels, bit 1 = lean tile kernel (RN_FFT_LEAN, read once; tuning)
+static int fft_lean() {
+    static const int value = [] {
+        const char* env = getenv("RN_FFT_LEAN");
+        return env ? atoi(env) : 0;
+    }();
+    return value;
 }
 
 static fft::OutSpec plain_out() {
@@ -373,7 +384,8 @@ static int launch_level(const rn_spectrum_plan* p, double2* X, int nseq, int lev
     P.out = out;
     P.tw = plan_twiddles(p);
     const int64_t grid = (int64_t)nseq * (p->Lh >> kLog2E);
-    fft::level_kernel<SGN><<<(unsigned)grid, kNT, fft::kTileSmemBytes, stream>>>(P);
+    if (fft_lean() & 1) fft::level_kernel<SGN, true><<<(unsigned)grid, kNT, fft::kTileSmemBytes, stream>>>(P);
+    else fft::level_kernel<SGN, false><<<(unsigned)grid, kNT, fft::kTileSmemBytes, stream>>>(P);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     return RN_OK;
@@ -401,8 +413,9 @@ static int run_convolution(const rn_spectrum_plan* p, double2* X, int nseq, int6
     T.out = p->nlev == 0 ? out : plain;
     T.tw = plan_twiddles(p);
     const unsigned grid = (unsigned)((int64_t)nseq * T.tiles_per_seq);
-    if (hout) fft::tile_kernel<true><<<grid, kNT, fft::kTileSmemBytes, stream>>>(T);
-    else fft::tile_kernel<false><<<grid, kNT, fft::kTileSmemBytes, stream>>>(T);
+    if (hout) fft::tile_kernel<true, false><<<grid, kNT, fft::kTileSmemBytes, stream>>>(T);
+    else if (fft_lean() & 2) fft::tile_kernel<false, true><<<grid, kNT, fft::kTileSmemBytes, stream>>>(T);
+    else fft::tile_kernel<false, false><<<grid, kNT, fft::kTileSmemBytes, stream>>>(T);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     if (hout) return RN_OK;

@@ -1,22 +1,33 @@
 """Frame sharding across GPUs (one process per GPU, ``torch.distributed``).
 
-``calc_polarizabilities`` has no cross-frame term, so frames shard naturally: rank r
-evaluates the contiguous block ``shard_bounds(S, G, r)`` with the model tables replicated.
-The only exchange step is one all-gather of the per-rank (S_r,3,3) blocks (72 B/frame), after
-which every rank holds the full series that ``MDRamanSpectrum`` owns
-(``ramannoodle/spectrum/_raman.py:212-216``); ``np.diff`` across shard boundaries needs no
-halo because it runs after the gather.
+``calc_polarizabilities`` has no cross-frame term, so frames shard naturally: rank r evaluates the
+contiguous block ``shard_bounds(S, G, r)`` with the model tables replicated
+(``ramannoodle/pmodel/_interpolation.py:191-252``).  ``MDRamanSpectrum.measure``
+(``ramannoodle/spectrum/_raman.py:241-309``) is global in S; here its single chirp-z transform is
+SHARED by the ranks (decimation in frequency at rank level, ``csrc/rn_spectrum.cu``):
+
+1. the evaluation kernels store every row of the (S,3,3) series straight to the rank whose spectrum
+   stage consumes it (peer stores over NVLink into symmetric memory; every row has one or two
+   destinations, so the series is never all-gathered);
+2. ``pack`` (np.diff, signal packing, chirp, G-point DFT over the blocks) stores residue r into rank
+   r's work buffer; 3. every rank runs its local length-L/G convolution and stores the result to the
+   ranks owning the output blocks; 4. ``final`` finishes its block and stores P = sum |y|^2 to every
+   rank; 5. every rank forms the intensities.  Device-side barriers separate the steps; there is no
+   NCCL collective on the path.  ``polarizability_ts`` all-gathers the series lazily when read.
+
+Without symmetric memory (CPU tensors, gloo, other backends) the local block is evaluated, one
+``all_gather_into_tensor`` assembles the series and every rank runs the single-GPU ``measure``.
 """
 from __future__ import annotations
 
 import ctypes
-import os
+import warnings
 
 from . import _lib
 from .abstract import Dynamics
 from .dynamics import Trajectory
 from .exceptions import get_type_error
-from .spectrum import MDRamanSpectrum, _get_plan, _stream
+from .spectrum import MDRamanSpectrum, _stream
 
 
 def shard_bounds(num_frames: int, world_size: int, rank: int) -> tuple[int, int]:
@@ -26,6 +37,23 @@ def shard_bounds(num_frames: int, world_size: int, rank: int) -> tuple[int, int]
     block = -(-num_frames // world_size)
     start = min(rank * block, num_frames)
     return start, min(start + block, num_frames)
+
+
+def transform_group_size(world_size: int) -> int:
+    """Ranks that share the chirp-z transform: the largest power of two <= min(world, 8); the other
+    ranks evaluate their frames and receive the spectrum."""
+    if world_size < 1:
+        raise ValueError("invalid world_size")
+    group = 1
+    while group * 2 <= min(world_size, 8):
+        group *= 2
+    return group
+
+
+def route_owner(frame: int, period: int, width: int) -> int:
+    """Rank whose ``pack`` stage consumes difference signal ``frame`` (it needs rows ``frame`` and
+    ``frame + 1`` of the series): ``include/ramannoodle_b200.h: rn_spectrum_dist_route``."""
+    return (frame % period) // width
 
 
 def allgather_series(local_series, num_frames: int, group=None):
@@ -56,131 +84,189 @@ def allgather_series(local_series, num_frames: int, group=None):
     return full[:num_frames]
 
 
-_SYMMETRIC_SERIES: dict = {}
+class SymmetricMemoryUnavailable(RuntimeError):
+    """Symmetric memory (peer-mapped buffers over NVLink) cannot be used by this process group."""
 
 
-def symmetric_series(num_frames: int, device, group=None):
-    """A (S,3,3) fp64 series buffer in symmetric memory (the same allocation on every rank of
-    ``group``, each rank's copy mapped into every other rank's address space over NVLink), plus its
-    rendezvous handle.  Cached per (S, device, group): the rendezvous is a collective."""
+_UNAVAILABLE_WARNED = False
+
+
+def _all_ranks_agree(ok: bool, device, group) -> bool:
+    """True only if ``ok`` holds on every rank (a rank-local failure must not split the ranks between
+    two different collective schedules)."""
     import torch  # pylint: disable=import-outside-toplevel
     import torch.distributed as dist  # pylint: disable=import-outside-toplevel
-    import torch.distributed._symmetric_memory as symm_mem  # pylint: disable=import-outside-toplevel
 
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(flag.item()))
+
+
+class _SharedContext:
+    """Everything the shared spectrum of one (S, device, group) needs: the dist plan and ONE symmetric
+    allocation holding this rank's full-layout series buffer, work buffer, receive buffer and power
+    buffer (cached: allocation and rendezvous are collectives)."""
+
+    def __init__(self, num_frames: int, device, group) -> None:
+        import torch  # pylint: disable=import-outside-toplevel
+        import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+
+        self.num_frames = int(num_frames)
+        self.device = device
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        index = int(device.index if device.index is not None else torch.cuda.current_device())
+        lib = _lib.lib()
+        handle = ctypes.c_void_p()
+        _lib.check(lib.rn_spectrum_plan_create_dist(self.num_frames, index, self.world, self.rank, ctypes.byref(handle)),
+                   "rn_spectrum_plan_create_dist")
+        self.plan = handle
+        sizes = [ctypes.c_int64() for _ in range(3)]
+        _lib.check(lib.rn_spectrum_dist_sizes(self.plan, *[ctypes.byref(v) for v in sizes]), "rn_spectrum_dist_sizes")
+        period, width = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(lib.rn_spectrum_dist_route(self.plan, ctypes.byref(period), ctypes.byref(width)),
+                   "rn_spectrum_dist_route")
+        self.period, self.width = int(period.value), int(width.value)
+        self.transform_ranks = self.period // self.width
+
+        def align(nbytes: int) -> int:
+            return (nbytes + 255) // 256 * 256
+
+        series_bytes = align(self.num_frames * 72)
+        self.offsets = {"series": 0, "work": series_bytes, "recv": series_bytes + align(sizes[0].value),
+                        "power": series_bytes + align(sizes[0].value) + align(sizes[1].value)}
+        total = self.offsets["power"] + align(sizes[2].value)
+        pg = group if group is not None else dist.group.WORLD
+        ok = True
+        self.buffer = self.handle = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem  # pylint: disable=import-outside-toplevel
+
+            self.buffer = symm_mem.empty(total // 8, dtype=torch.float64, device=device)
+            self.handle = symm_mem.rendezvous(self.buffer, group=pg.group_name)
+        except (RuntimeError, ImportError, AttributeError, NotImplementedError) as exc:
+            ok = False
+            self.error = exc
+        if not _all_ranks_agree(ok, device, group):
+            self.close()
+            raise SymmetricMemoryUnavailable(str(getattr(self, "error", "another rank could not allocate symmetric memory")))
+        self.generation = 0
+        self.local_base = int(self.buffer.data_ptr())
+        self.peer_bases = [int(self.handle.buffer_ptrs[r]) for r in range(self.world)]
+
+    def ptr(self, rank: int, name: str) -> int:
+        return self.peer_bases[rank] + self.offsets[name]
+
+    def table(self, name: str, count: int):
+        return (ctypes.c_void_p * count)(*[ctypes.c_void_p(self.ptr(r, name)) for r in range(count)])
+
+    def series_view(self, start: int, stop: int):
+        """This rank's rows [start, stop) of its own series buffer as a (n,3,3) tensor."""
+        return self.buffer[start * 9: stop * 9].view(stop - start, 3, 3)
+
+    def barrier(self) -> None:
+        self.handle.barrier()
+
+    def close(self) -> None:
+        if getattr(self, "plan", None):
+            _lib.lib().rn_spectrum_plan_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+_SHARED: dict = {}
+
+
+def _shared_context(num_frames: int, device, group):
+    """The cached ``_SharedContext``, or None if symmetric memory is unavailable (every rank agrees)."""
+    import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+
+    global _UNAVAILABLE_WARNED  # pylint: disable=global-statement
     pg = group if group is not None else dist.group.WORLD
     key = (int(num_frames), str(device), pg.group_name)
-    entry = _SYMMETRIC_SERIES.get(key)
-    if entry is None:
-        tensor = symm_mem.empty((int(num_frames), 3, 3), dtype=torch.float64, device=device)
-        handle = symm_mem.rendezvous(tensor, group=pg.group_name)
-        entry = (tensor, handle)
-        _SYMMETRIC_SERIES.clear()  # one live buffer: they are as large as the series
-        _SYMMETRIC_SERIES[key] = entry
-    return entry
+    if key in _SHARED:
+        return _SHARED[key]
+    try:
+        ctx = _SharedContext(num_frames, device, group)
+    except SymmetricMemoryUnavailable as exc:
+        if not _UNAVAILABLE_WARNED:
+            warnings.warn(f"symmetric memory unavailable ({exc}); using the all-gather path", RuntimeWarning)
+            _UNAVAILABLE_WARNED = True
+        ctx = None
+    _SHARED.clear()  # one live context: its buffers are as large as the series
+    _SHARED[key] = ctx
+    return ctx
 
 
-def spectrum_parts(world_size: int, rank: int) -> list[int]:
-    """Which of the three packed transforms of ``measure`` rank ``rank`` computes
-    (``include/ramannoodle_b200.h: rn_md_spectrum_part``): round-robin over the ranks."""
-    return [part for part in range(3) if part % world_size == rank]
-
-
-def spectrum_half_units(world_size: int, rank: int):
-    """Split-transform schedule of ``measure`` (``rn_md_spectrum_half``): each of the three packed
-    transforms is two half-length transforms (output residues 0/1) run by a pair of ranks that read
-    each other's result.  Returns ``(units, partner)`` with ``units`` the ``(part, residue)`` pairs
-    of this rank (slot order) and ``partner`` the rank holding the other residue of every unit, or
-    ``None`` when the world size does not profit (then whole parts are dealt out, ``spectrum_parts``).
-
-    2 ranks: rank r runs residue r of all three parts (3 half transforms each instead of 2 + 1 full
-    ones).  6 or more ranks: ranks 2p and 2p+1 run the residues of part p (one half transform each
-    instead of one full transform on three ranks); further ranks only take part in the barriers."""
-    if not 0 <= rank < world_size:
-        raise ValueError("invalid rank/world_size")
-    if world_size == 2:
-        return [(part, rank) for part in range(3)], 1 - rank
-    if world_size >= 6:
-        if rank < 6:
-            return [(rank // 2, rank % 2)], rank ^ 1
-        return [], None
-    return None
-
-
-_SYMMETRIC_HALVES: dict = {}
-
-
-def symmetric_halves(slots: int, half_length: int, device, group=None):
-    """``(slots, L/2, 2)`` fp64 buffer in symmetric memory for the half-transform results, plus its
-    rendezvous handle (cached: the rendezvous is a collective)."""
-    import torch  # pylint: disable=import-outside-toplevel
-    import torch.distributed as dist  # pylint: disable=import-outside-toplevel
-    import torch.distributed._symmetric_memory as symm_mem  # pylint: disable=import-outside-toplevel
-
-    pg = group if group is not None else dist.group.WORLD
-    key = (int(slots), int(half_length), str(device), pg.group_name)
-    entry = _SYMMETRIC_HALVES.get(key)
-    if entry is None:
-        tensor = symm_mem.empty((int(slots), int(half_length), 2), dtype=torch.float64, device=device)
-        handle = symm_mem.rendezvous(tensor, group=pg.group_name)
-        entry = (tensor, handle)
-        _SYMMETRIC_HALVES.clear()
-        _SYMMETRIC_HALVES[key] = entry
-    return entry
+def clear_shared_contexts() -> None:
+    for ctx in _SHARED.values():
+        if ctx is not None:
+            ctx.close()
+    _SHARED.clear()
 
 
 class ShardedMDRamanSpectrum(MDRamanSpectrum):
-    """``MDRamanSpectrum`` whose ``measure`` is spread over the ranks of a process group.
+    """``MDRamanSpectrum`` of a frame-sharded series.
 
-    Every rank holds the full (S,3,3) series (after the all-gather).  The orientational average
-    45 a^2 + 7 g^2 (``ramannoodle/spectrum/_raman.py:286-297``) is a sum of three independent
-    packed chirp-z transforms; rank r computes parts ``spectrum_parts(G, r)``, the (P,) partial
-    intensities are summed with one all-reduce, and every rank applies the wavenumber grid and
-    the optional corrections.  With G >= 3 the spectrum stage costs one transform instead of three.
+    With a shared context (NCCL group + symmetric memory) the rows sit where the shared transform
+    needs them and ``measure`` runs steps 2-5 of the module docstring; ``polarizability_ts`` gathers
+    the series on first access.  Otherwise every rank holds the whole series (all-gather path) and
+    ``measure`` is the single-GPU one.
     """
 
-    def __init__(self, polarizability_ts, timestep: float, group=None, split_transforms: bool = True):
-        super().__init__(polarizability_ts, timestep)
+    def __init__(self, polarizability_ts, timestep: float, group=None, context=None, generation: int = 0,
+                 bounds=None):
+        if context is None:
+            super().__init__(polarizability_ts, timestep)
+        else:  # the local block only; the full series is assembled on demand
+            self._polarizability_ts = None
+            self._timestep = timestep
         self._group = group
-        # RN_SPLIT_TRANSFORMS=0: A/B switch back to whole transforms per rank
-        self._split_transforms = bool(split_transforms) and os.environ.get("RN_SPLIT_TRANSFORMS", "1") != "0"
+        self._context = context
+        self._generation = generation
+        self._bounds = bounds
 
-    def _measure_split(self, series, plan, total, world, rank, device) -> bool:
-        """Half-transform schedule (``spectrum_half_units``); False if it does not apply here."""
-        import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+    def _check_live(self) -> None:
+        if self._context.generation != self._generation:
+            raise RuntimeError("the shared series buffer was overwritten by a later get_raman_spectrum() call; "
+                               "measure() / polarizability_ts must be used before evaluating again")
 
-        schedule = spectrum_half_units(world, rank) if self._split_transforms else None
-        if schedule is None or dist.get_backend(self._group) != "nccl":
-            return False
-        units, partner = schedule
-        half_length = int(_lib.lib().rn_spectrum_half_length(plan.handle))
-        slots = 3 if world == 2 else 1
-        try:
-            zbuf, handle = symmetric_halves(slots, half_length, series.device, self._group)
-        except Exception:  # pylint: disable=broad-except  (no symmetric-memory support on this system)
-            return False
-        stream = _stream(device)
-        handle.barrier()  # the partner is done reading the previous contents
-        for slot, (part, residue) in enumerate(units):
-            status = _lib.lib().rn_md_spectrum_half(plan.handle, ctypes.c_void_p(series.data_ptr()), part, residue,
-                                                    ctypes.c_void_p(zbuf[slot].data_ptr()), 1 if slot > 0 else 0, stream)
-            _lib.check(status, "rn_md_spectrum_half")
-        handle.barrier()  # both residues of every unit are complete
-        for slot, (part, residue) in enumerate(units):
-            own = int(zbuf[slot].data_ptr())
-            other = int(handle.buffer_ptrs[partner]) + slot * half_length * 16
-            res0, res1 = (own, other) if residue == 0 else (other, own)
-            status = _lib.lib().rn_md_spectrum_half_combine(plan.handle, part, residue, ctypes.c_void_p(res0),
-                                                            ctypes.c_void_p(res1), ctypes.c_void_p(total.data_ptr()),
-                                                            1 if slot > 0 else 0, stream)
-            _lib.check(status, "rn_md_spectrum_half_combine")
-        return True
+    @property
+    def local_polarizability_ts(self):
+        """This rank's (S_r,3,3) block of the series (a CUDA tensor)."""
+        if self._context is None:
+            start, stop = self._bounds if self._bounds else (0, len(self._polarizability_ts))
+            return self._polarizability_ts[start:stop]
+        self._check_live()
+        return self._context.series_view(*self._bounds)
+
+    def _gathered(self):
+        if self._polarizability_ts is None:
+            self._check_live()
+            self._polarizability_ts = allgather_series(self.local_polarizability_ts, self._context.num_frames,
+                                                       self._group).clone()
+        return self._polarizability_ts
+
+    @property
+    def polarizability_ts(self):
+        """The whole (S,3,3) series as numpy (a collective on first access: every rank must read it)."""
+        if self._context is not None:
+            return self._gathered().cpu().numpy()
+        return MDRamanSpectrum.polarizability_ts.fget(self)
 
     # pylint: disable=too-many-arguments,too-many-positional-arguments,too-many-locals
     def measure_device(self, orientation="polycrystalline", laser_correction=False, laser_wavelength=522,
                        bose_einstein_correction=False, temperature=300):
         import torch  # pylint: disable=import-outside-toplevel
-        import torch.distributed as dist  # pylint: disable=import-outside-toplevel
 
+        if self._context is None:
+            return super().measure_device(orientation, laser_correction, laser_wavelength,
+                                          bose_einstein_correction, temperature)
         if orientation != "polycrystalline":
             raise NotImplementedError("only polycrystalline spectra are supported for now")
         if laser_correction:
@@ -196,54 +282,36 @@ class ShardedMDRamanSpectrum(MDRamanSpectrum):
                     raise ValueError(f"invalid temperature: {temperature} <= 0")
             except TypeError as exc:
                 raise get_type_error("temperature", temperature, "float") from exc
-        series = self._device_series()
-        num_frames = int(series.shape[0])
-        if num_frames < 2:
+        ctx = self._context
+        self._check_live()
+        if ctx.num_frames < 2:
             raise ValueError("polarizability_ts must contain at least 2 configurations")
-        device = int(series.device.index or 0)
-        world, rank = dist.get_world_size(self._group), dist.get_rank(self._group)
-        points = int(_lib.lib().rn_spectrum_num_points(num_frames))
+        lib = _lib.lib()
+        device = int(ctx.device.index or 0)
+        points = int(lib.rn_spectrum_num_points(ctx.num_frames))
         with torch.cuda.device(device):
-            # element `points` of the reduced vector carries the sharded series-energy constant
-            total = torch.zeros(points + 1, dtype=torch.float64, device=series.device)
-            wavenumbers = torch.empty(points, dtype=torch.float64, device=series.device)
-            intensities = torch.empty(points, dtype=torch.float64, device=series.device)
-            if points > 0:
-                plan = _get_plan(num_frames, device)
-                lib = _lib.lib()
-                # the energies (one pass over the whole series) shard over ranks: every rank sums the
-                # difference signals of its block and the constant rides along with the all-reduce
-                shard_energy = world > 1
-                if shard_energy:
-                    _lib.check(lib.rn_spectrum_set_energy_mode(plan.handle, 1), "rn_spectrum_set_energy_mode")
-                try:
-                    split = world > 1 and self._measure_split(series, plan, total, world, rank, device)
-                    parts = [] if split else spectrum_parts(world, rank)
-                    if parts:
-                        partial = torch.empty(points, dtype=torch.float64, device=series.device)
-                        for part in parts:
-                            status = lib.rn_md_spectrum_part(plan.handle, ctypes.c_void_p(series.data_ptr()), part,
-                                                             ctypes.c_void_p(partial.data_ptr()), _stream(device))
-                            _lib.check(status, "rn_md_spectrum_part")
-                            total[:points] += partial
-                    if shard_energy:
-                        begin, end = shard_bounds(num_frames - 1, world, rank)
-                        status = lib.rn_series_energy_constant(
-                            plan.handle, ctypes.c_void_p(series.data_ptr()), begin, end,
-                            ctypes.c_void_p(total.data_ptr() + 8 * points), _stream(device))
-                        _lib.check(status, "rn_series_energy_constant")
-                finally:
-                    if shard_energy:
-                        lib.rn_spectrum_set_energy_mode(plan.handle, 0)
-                if world > 1:
-                    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self._group)
-                    total[:points] += total[points]
-                status = lib.rn_md_spectrum_finish(
-                    num_frames, ctypes.c_void_p(total.data_ptr()), float(self._timestep),
-                    1 if laser_correction else 0, float(laser_wavelength) if laser_correction else 0.0,
-                    1 if bose_einstein_correction else 0, float(temperature) if bose_einstein_correction else 0.0,
-                    ctypes.c_void_p(wavenumbers.data_ptr()), ctypes.c_void_p(intensities.data_ptr()), _stream(device))
-                _lib.check(status, "rn_md_spectrum_finish")
+            wavenumbers = torch.empty(points, dtype=torch.float64, device=ctx.device)
+            intensities = torch.empty(points, dtype=torch.float64, device=ctx.device)
+            if points == 0:
+                return wavenumbers, intensities
+            stream = _stream(device)
+            group = ctx.transform_ranks
+            _lib.check(lib.rn_spectrum_dist_pack(ctx.plan, ctypes.c_void_p(ctx.ptr(ctx.rank, "series")),
+                                                 ctx.table("work", group), stream), "rn_spectrum_dist_pack")
+            ctx.barrier()  # every residue of every block has landed in the work buffers
+            _lib.check(lib.rn_spectrum_dist_transform(ctx.plan, ctypes.c_void_p(ctx.ptr(ctx.rank, "work")),
+                                                      ctx.table("recv", group), stream), "rn_spectrum_dist_transform")
+            ctx.barrier()  # every rank holds all residues of its output block
+            _lib.check(lib.rn_spectrum_dist_final(ctx.plan, ctypes.c_void_p(ctx.ptr(ctx.rank, "recv")),
+                                                  ctx.table("power", ctx.world), ctx.world, stream),
+                       "rn_spectrum_dist_final")
+            ctx.barrier()  # P and the energy shares are complete on every rank
+            status = lib.rn_spectrum_dist_combine(
+                ctx.plan, ctypes.c_void_p(ctx.ptr(ctx.rank, "power")), float(self._timestep),
+                1 if laser_correction else 0, float(laser_wavelength) if laser_correction else 0.0,
+                1 if bose_einstein_correction else 0, float(temperature) if bose_einstein_correction else 0.0,
+                ctypes.c_void_p(wavenumbers.data_ptr()), ctypes.c_void_p(intensities.data_ptr()), stream)
+            _lib.check(status, "rn_spectrum_dist_combine")
         return wavenumbers, intensities
 
 
@@ -280,20 +348,16 @@ class ShardedTrajectory(Dynamics):
     def num_frames(self) -> int:
         return self._num_frames
 
-    def get_raman_spectrum(self, polarizability_model, fused: bool = True,
-                           reuse_series_buffer: bool = False) -> MDRamanSpectrum:
-        """Evaluate the local block and assemble the full (S,3,3) series on every rank; returns a
-        ``ShardedMDRamanSpectrum`` (its ``measure`` is spread over the ranks too).
+    def get_raman_spectrum(self, polarizability_model, shared: bool = True) -> MDRamanSpectrum:
+        """Evaluate the local block; returns a ``ShardedMDRamanSpectrum``.
 
-        ``fused=True`` (default, CUDA + NCCL groups with this package's models): the series lives
-        in symmetric memory and the evaluation kernels store every row to all ranks' copies over
-        NVLink themselves, so the all-gather overlaps the evaluation; two device-side barriers
-        bracket the stores.  Otherwise (or if symmetric memory is unavailable) the local block is
-        evaluated first and one ``all_gather_into_tensor`` assembles the series.
-        ``reuse_series_buffer=True`` hands out the symmetric buffer itself (overwritten by the next
-        call) instead of a copy."""
-        if fused:
-            spectrum = self._get_raman_spectrum_fused(polarizability_model, reuse_series_buffer)
+        ``shared=True`` (default; CUDA + NCCL groups of at most 8 ranks with this package's models):
+        the rows are routed to the ranks that consume them and ``measure`` runs one chirp-z transform
+        shared by the ranks.  The spectrum object refers to buffers that the next ``get_raman_spectrum``
+        call of the same size overwrites.  Otherwise, or if symmetric memory is unavailable: one
+        ``all_gather_into_tensor`` assembles the series on every rank."""
+        if shared:
+            spectrum = self._get_raman_spectrum_shared(polarizability_model)
             if spectrum is not None:
                 return spectrum
         local = self._local.get_raman_spectrum(polarizability_model)
@@ -302,36 +366,34 @@ class ShardedTrajectory(Dynamics):
             import torch  # pylint: disable=import-outside-toplevel
 
             series = torch.from_numpy(series)
-        full = allgather_series(series, self._num_frames, self._group)
-        return ShardedMDRamanSpectrum(full, self._local.timestep, self._group)
+        import torch.distributed as dist  # pylint: disable=import-outside-toplevel
 
-    def _get_raman_spectrum_fused(self, polarizability_model, reuse_series_buffer: bool):
+        full = allgather_series(series, self._num_frames, self._group)
+        bounds = shard_bounds(self._num_frames, dist.get_world_size(self._group), dist.get_rank(self._group))
+        return ShardedMDRamanSpectrum(full, self._local.timestep, self._group, bounds=bounds)
+
+    def _get_raman_spectrum_shared(self, polarizability_model):
         import torch  # pylint: disable=import-outside-toplevel
         import torch.distributed as dist  # pylint: disable=import-outside-toplevel
 
-        multi = getattr(polarizability_model, "calc_polarizabilities_multi", None)
-        if multi is None or not torch.cuda.is_available() or dist.get_backend(self._group) != "nccl":
+        routed = getattr(polarizability_model, "calc_polarizabilities_routed", None)
+        if routed is None or not torch.cuda.is_available() or dist.get_backend(self._group) != "nccl":
             return None
         world, rank = dist.get_world_size(self._group), dist.get_rank(self._group)
-        if world == 1 or world > 8:
+        if world == 1 or world > 8 or self._num_frames < 2:
             return None
         positions = self._local._positions_ts  # pylint: disable=protected-access
         device = positions.device if hasattr(positions, "data_ptr") else torch.device("cuda", torch.cuda.current_device())
-        try:
-            series, handle = symmetric_series(self._num_frames, device, self._group)
-        except Exception:  # pylint: disable=broad-except  (no symmetric-memory support on this system)
+        ctx = _shared_context(self._num_frames, device, self._group)
+        if ctx is None:
             return None
-        start, _ = shard_bounds(self._num_frames, world, rank)
-        order = [rank] + [r for r in range(world) if r != rank]  # local copy first
-        ptrs = [int(handle.buffer_ptrs[r]) + start * 72 for r in order]
-        dup = int(os.environ.get("RN_DEBUG_DUP_PEERS", "0"))  # timing aid: emulate more peers on a 2-GPU box
-        while dup and len(ptrs) < min(dup + 1, 8):
-            ptrs.append(ptrs[1])
-        handle.barrier()  # every rank is done with the previous contents of the buffers
+        start, stop = shard_bounds(self._num_frames, world, rank)
+        peers = [0 if r == rank else ctx.ptr(r, "series") for r in range(world)]
         try:
-            multi(positions, ptrs)
+            routed(positions, ctx.ptr(rank, "series") + start * 72, peers, start, ctx.period, ctx.width)
         except ValueError as exc:
             raise ValueError("polarizability_model and trajectory are incompatible") from exc
-        handle.barrier()  # every rank's rows have landed everywhere
-        full = series if reuse_series_buffer else series.clone()
-        return ShardedMDRamanSpectrum(full, self._local.timestep, self._group)
+        ctx.generation += 1
+        ctx.barrier()  # every rank's rows have landed where they are consumed
+        return ShardedMDRamanSpectrum(None, self._local.timestep, self._group, context=ctx,
+                                      generation=ctx.generation, bounds=(start, stop))

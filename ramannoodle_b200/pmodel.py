@@ -264,9 +264,57 @@ class InterpolationModel(PolarizabilityModel):
         self._check_dummy()
         positions = np.ascontiguousarray(positions_batch, dtype=np.float64)
         native = self._native_model()
+        import torch  # pylint: disable=import-outside-toplevel
+
+        # the pipeline's private streams start after the work already enqueued on the current stream
+        # (e.g. the cross-rank barrier in front of this call)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(native.device).cuda_stream)
         status = _lib.lib().rn_calc_polarizabilities_host_multi(native.handle, _ptr(positions), positions.shape[0],
-                                                                outputs, count, 0)
+                                                                outputs, count, 0, stream)
         _lib.check(status, "rn_calc_polarizabilities_host_multi")
+
+    # pylint: disable=too-many-arguments,too-many-positional-arguments
+    def calc_polarizabilities_routed(self, positions_batch, local_ptr: int, peer_series, first_frame: int,
+                                     period: int, width: int) -> None:
+        """Evaluate this rank's block and route the rows for the shared multi-GPU spectrum
+        (``rn_calc_polarizabilities_routed``): rows go to ``local_ptr`` (this rank's block inside its own
+        full series buffer) and, written by the kernels over NVLink, to the series buffers
+        ``peer_series[r]`` (base pointers, 0 for this rank) of the ranks whose spectrum stage consumes them —
+        row ``n`` to ranks ``(n % period) // width`` and ``((n - 1) % period) // width``."""
+        import torch  # pylint: disable=import-outside-toplevel
+
+        world = len(peer_series)
+        if not 1 <= world <= 8:
+            raise ValueError("between 1 and 8 ranks")
+        peers = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(ptr)) if ptr else None for ptr in peer_series])
+        if _is_torch_tensor(positions_batch):
+            if not positions_batch.is_cuda:
+                raise get_type_error("positions", positions_batch, "ndarray or CUDA tensor")
+            if positions_batch.ndim != 3 or tuple(positions_batch.shape[1:]) != (self.num_atoms, 3):
+                raise get_shape_error("positions", positions_batch, f"(_,{self.num_atoms},3)")
+            self._check_dummy()
+            data = positions_batch.to(torch.float64).contiguous()
+            device = self._resolve_device(data)
+            native = self._native_model(device)
+            with torch.cuda.device(device):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+                status = _lib.lib().rn_calc_polarizabilities_routed(
+                    native.handle, ctypes.c_void_p(data.data_ptr()), int(data.shape[0]), ctypes.c_void_p(int(local_ptr)),
+                    peers, world, int(first_frame), int(period), int(width), stream)
+            _lib.check(status, "rn_calc_polarizabilities_routed")
+            return
+        if not isinstance(positions_batch, np.ndarray):
+            raise get_type_error("positions", positions_batch, "ndarray")
+        if positions_batch.ndim != 3 or positions_batch.shape[1:] != (self.num_atoms, 3):
+            raise get_shape_error("positions", positions_batch, f"(_,{self.num_atoms},3)")
+        self._check_dummy()
+        positions = np.ascontiguousarray(positions_batch, dtype=np.float64)
+        native = self._native_model()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(native.device).cuda_stream)
+        status = _lib.lib().rn_calc_polarizabilities_host_routed(
+            native.handle, _ptr(positions), positions.shape[0], ctypes.c_void_p(int(local_ptr)), peers, world,
+            int(first_frame), int(period), int(width), 0, stream)
+        _lib.check(status, "rn_calc_polarizabilities_host_routed")
 
     def get_polarizability(self, cart_displacements):
         """Polarizabilities from precomputed Cartesian displacements (S,N,3) or (S,3N) in Å

@@ -13,30 +13,22 @@ import torch.multiprocessing as mp
 from ramannoodle_b200.distributed import shard_bounds
 
 
-def test_spectrum_schedules():
-    """Host-side schedules of the sharded measure: whole parts (``spectrum_parts``) and the two-rank
-    split of every packed transform (``spectrum_half_units``)."""
-    from ramannoodle_b200.distributed import spectrum_half_units, spectrum_parts
+def test_transform_group_and_routing():
+    """Host-side schedule of the shared spectrum: which ranks share the transform and which rank
+    consumes which difference signal (``rn_spectrum_dist_route``; mirrored by ``route_owner``)."""
+    from ramannoodle_b200.distributed import route_owner, transform_group_size
 
-    for world in range(1, 9):
-        assert sorted(sum((spectrum_parts(world, r) for r in range(world)), [])) == [0, 1, 2]
-    for world in (2, 6, 7, 8):
-        owned = []
-        for rank in range(world):
-            units, partner = spectrum_half_units(world, rank)
-            owned += units
-            if units:
-                other_units, other_partner = spectrum_half_units(world, partner)
-                assert other_partner == rank and other_units == [(p, 1 - r) for p, r in units]
-            else:
-                assert partner is None and world > 6 and rank >= 6
-        assert sorted(owned) == [(p, r) for p in range(3) for r in range(2)]
-    assert spectrum_half_units(2, 1) == ([(0, 1), (1, 1), (2, 1)], 0)
-    assert spectrum_half_units(8, 5) == ([(2, 1)], 4)
-    for world in (1, 3, 4, 5):
-        assert spectrum_half_units(world, 0) is None
+    assert [transform_group_size(w) for w in range(1, 10)] == [1, 2, 2, 4, 4, 4, 4, 8, 8]
     with pytest.raises(ValueError):
-        spectrum_half_units(2, 2)
+        transform_group_size(0)
+    # 8 ranks, S = 8e6: L = 2^24, period = L/8 = 2^21, width = 2^18; every difference signal n < M has
+    # exactly one owner and the owners' blocks tile every period
+    period, width = 1 << 21, 1 << 18
+    for frame in (0, 1, width - 1, width, period - 1, period, 3 * period + 5 * width + 17, 7_999_998):
+        owner = route_owner(frame, period, width)
+        assert 0 <= owner < 8 and owner == ((frame % period) // width)
+    owners = [route_owner(n, 4096, 512) for n in range(0, 3 * 4096, 512)]
+    assert owners == [0, 1, 2, 3, 4, 5, 6, 7] * 3
 
 
 def test_shard_bounds_partition_frames():
@@ -87,6 +79,65 @@ def _worker(rank, world, port, frames, queue):
         queue.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
+
+
+class _OracleBackedModel:
+    """Duck-typed polarizability model evaluated by the oracle (no GPU): drives the sharded trajectory
+    through the all-gather path."""
+
+    def __init__(self, omodel):
+        self._omodel = omodel
+
+    def calc_polarizabilities(self, positions_batch):
+        from oracle import numpy_port as ora
+
+        return ora.calc_polarizabilities(self._omodel, np.asarray(positions_batch))
+
+
+def _trajectory_worker(rank, world, port, frames, queue):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import numpy_port as ora
+        from ramannoodle_b200 import synthetic
+        from ramannoodle_b200.distributed import ShardedMDRamanSpectrum, ShardedTrajectory
+
+        state = synthetic.make_model("TiO2", "art", num_dofs=12)
+        omodel = ora.OracleModel(state.ref_positions, state.lattice, state.ref_polarizability,
+                                 list(state.basis_vectors), list(state.splines), state.mask)
+        positions = synthetic.make_trajectory("TiO2", frames, seed=5)
+        start, stop = shard_bounds(frames, world, rank)
+        sharded = ShardedTrajectory(positions[start:stop], 2.0, frames)
+        spectrum = sharded.get_raman_spectrum(_OracleBackedModel(omodel))  # gloo -> all-gather path
+        want = ora.calc_polarizabilities(omodel, ora.trajectory_positions(positions))
+        ok = isinstance(spectrum, ShardedMDRamanSpectrum) and spectrum.timestep == 2.0
+        ok = ok and np.array_equal(spectrum.polarizability_ts, want)
+        ok = ok and np.array_equal(np.asarray(spectrum.local_polarizability_ts), want[start:stop])
+        try:
+            ShardedTrajectory(positions[start:stop][:-1], 2.0, frames)
+            ok = False
+        except ValueError:
+            pass
+        queue.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("frames", [50, 33])
+def test_sharded_trajectory_allgather_path_world2(frames):
+    """ShardedTrajectory.get_raman_spectrum on a gloo group: local evaluation, one all-gather, every
+    rank holds the series the reference's MDRamanSpectrum would own."""
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_trajectory_worker, args=(r, 2, port, frames, queue)) for r in range(2)]
+    for proc in procs:
+        proc.start()
+    results = [queue.get(timeout=180) for _ in procs]
+    for proc in procs:
+        proc.join(timeout=60)
+        assert proc.exitcode == 0
+    assert sorted(results) == [(0, True), (1, True)]
 
 
 @pytest.mark.parametrize("frames", [64, 37])

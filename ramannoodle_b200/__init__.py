@@ -8,6 +8,7 @@ implemented as hand-written CUDA behind the C-ABI in ``include/ramannoodle_b200.
 from .abstract import Dynamics, PolarizabilityModel, RamanSpectrum
 from .dynamics import Phonons, Trajectory
 from .exceptions import NativeLibraryError, UserError
+from .dropin import install, uninstall
 from .pmodel import ARTModel, InterpolationModel, accelerate, calc_polarizabilities_sweep
 from .spectrum import (MDRamanSpectrum, PhononRamanSpectrum, calc_signal_spectrum, convolve_spectrum,
                        get_bose_einstein_correction, get_laser_correction)
@@ -15,6 +16,6 @@ from .state import ModelState
 
 __all__ = [
     "ARTModel", "Dynamics", "InterpolationModel", "MDRamanSpectrum", "ModelState", "NativeLibraryError",
-    "Phonons", "PhononRamanSpectrum", "PolarizabilityModel", "RamanSpectrum", "Trajectory", "UserError", "accelerate", "calc_signal_spectrum",
+    "Phonons", "PhononRamanSpectrum", "PolarizabilityModel", "RamanSpectrum", "Trajectory", "UserError", "accelerate", "calc_signal_spectrum", "install", "uninstall",
     "convolve_spectrum", "get_bose_einstein_correction", "get_laser_correction",
 ]

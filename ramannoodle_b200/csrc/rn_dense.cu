@@ -290,7 +290,7 @@ static int launch_tp_cfg(const rn_model* m, const double* d_in, bool wrap, bool 
         auto kern = dense_kernel_tp<DEG, NBK, FULL, W, A, 1>;                                                \
         RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
         kern<<<grid, 384, smem, stream>>>(d_in, m->d_ref_wrapped, V, m->d_tp_x0, m->d_tp_brk, num_frames, K, \
-                                          (int)m->v_cols, (int)m->dense_pad, accumulate ? 1 : 0,             \
+                                          (int)m->v_cols, (int)m->dense_pad, (int)m->num_dense, accumulate ? 1 : 0,             \
                                           split ? 1 : 0, mk, peers);                                         \
     }
     if (wrap) {
@@ -339,7 +339,7 @@ static int launch_v3_cfg(const rn_model* m, const double* d_in, bool wrap, bool 
         auto kern = dense_kernel_v3<DEG, PB, W, A>;                                                            \
         RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         kern<<<grid, 256, smem, stream>>>(d_in, m->d_ref_wrapped, V, m->d_piece_off, m->d_breaks, m->d_pieces, \
-                                          num_frames, K, (int)m->v_cols, (int)m->dense_pad, accumulate ? 1 : 0, a0, \
+                                          num_frames, K, (int)m->v_cols, (int)m->dense_pad, accumulate ? 1 : 0, a0,                     \
                                           d_alpha);                                                            \
     }
     if (wrap) {

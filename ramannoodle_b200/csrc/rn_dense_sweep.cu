@@ -52,7 +52,7 @@ static int launch_tp_sweep_cfg(const rn_model* const* models, const double* d_in
         auto kern = dense_kernel_tp<DEG, NBK, FULL, true, A, NG>;                                               \
         RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
         kern<<<grid, 384, smem, stream>>>(d_in, m->d_ref_wrapped, m->d_v_frac, m->d_tp_x0, m->d_tp_brk,         \
-                                          num_frames, K, (int)m->v_cols, (int)m->dense_pad, accumulate ? 1 : 0, \
+                                          num_frames, K, (int)m->v_cols, (int)m->dense_pad, (int)m->num_dense, accumulate ? 1 : 0, \
                                           split ? 1 : 0, mk, peers);                                            \
     }
     if (align16) RN_TP_SWEEP_LAUNCH(true) else RN_TP_SWEEP_LAUNCH(false)

@@ -53,7 +53,7 @@ template <int DEG, int NBK, bool FULL, bool WRAP, bool ALIGN16, int NG>
 __global__ void __launch_bounds__(384, 1)
     dense_kernel_tp(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ V,
                     const double* __restrict__ tp_x0, const double* __restrict__ tp_brk, int64_t num_frames, int K,
-                    int Kv, int Jpad, int accumulate, int split, TpMasks<NG> mk, AlphaPeers peers) {
+                    int Kv, int Jpad, int Jreal, int accumulate, int split, TpMasks<NG> mk, AlphaPeers peers) {
     constexpr int FT = 128;    // frames per tile: 8 MMA warps x 16
     constexpr int MMAW = 8;    // MMA warps (two per scheduler: one covers the other's LDS / barrier bubbles)
     constexpr int MTW = 2;     // 8-frame groups per MMA warp
@@ -192,6 +192,10 @@ __global__ void __launch_bounds__(384, 1)
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp;  // frames 16*wm .. 16*wm+15
     uint32_t consumed = 0;
+    // padding is not computed: the last DOF tile runs only the 8-DOF column groups that hold real DOFs,
+    // the last K chunk only the 4-element k-steps that hold real coordinates (warp-uniform predicates)
+    const int nt_last = (Jreal - (jtiles - 1) * kJT2 + 7) >> 3;
+    const int ks_last = (K - (chunks - 1) * kKC2 + 3) >> 2;
     for (int64_t tile = tile_begin; tile < tile_end; tile++) {
         const int64_t frame0 = tile * FT;
         const int jt_lo = (int)(max(u0, tile * jtiles) - tile * jtiles);
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(384, 1)
             for (int mt = 0; mt < MTW; mt++) af[0][mt] = a_src[mt * 8 * kRS2];
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) bf[0][nt] = b_src[nt * 8 * kRS2];
+            const int ntc = (jt == jtiles - 1) ? nt_last : 8;
+            const int ksc = (kc == chunks - 1) ? ks_last : kKC2 / 4;
 #pragma unroll
             for (int s = 0; s < kKC2 / 4; s++) {
                 const int cur = s & 1, nxt = cur ^ 1;
@@ -230,10 +236,15 @@ __global__ void __launch_bounds__(384, 1)
 #pragma unroll
                     for (int nt = 0; nt < 8; nt++) bf[nxt][nt] = b_src[nt * 8 * kRS2 + 4 * (s + 1)];
                 }
+                if (s < ksc) {
 #pragma unroll
-                for (int nt = 0; nt < 8; nt++)
+                    for (int nt = 0; nt < 8; nt++)
+                        if (nt < ntc) {
 #pragma unroll
-                    for (int mt = 0; mt < MTW; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[cur][mt], bf[cur][nt]);
+                            for (int mt = 0; mt < MTW; mt++)
+                                dmma884(acc[mt][nt][0], acc[mt][nt][1], af[cur][mt], bf[cur][nt]);
+                        }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive2(empty0 + 8 * st);  // stage may be refilled
@@ -248,6 +259,7 @@ __global__ void __launch_bounds__(384, 1)
                 // ---- chained-DMMA epilogue of this DOF tile ----
 #pragma unroll
                 for (int nt = 0; nt < 8; nt++) {
+                    if (nt >= ntc) continue;  // column groups of pure padding
 #pragma unroll
                     for (int c = 0; c < 2; c++) {
                         const int jl = jt_now * kJT2 + nt * 8 + 2 * t + c;  // DOF in this lane's k-slot

@@ -262,9 +262,12 @@ __global__ void __launch_bounds__(kNT, LEAN ? 3 : 2) tile_kernel(const __grid_co
     for (int m = 0; m < kPerThread / 8; m++) {
         const int pos0 = ((int)threadIdx.x + m * kNT) << 3;
         double2 h[8];
+        // the filter spectrum of a tile is stored [q][u] (element pos0 + q of butterfly u at q * 512 + u):
+        // consecutive threads read consecutive addresses
+        const int hu = (int)threadIdx.x + m * kNT;
         if (!FWD_ONLY) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) h[q] = __ldg(P.H + tile_base + pos0 + q);
+            for (int q = 0; q < 8; q++) h[q] = __ldg(P.H + tile_base + (q << 9) + hu);
         }
         double2 x[8];
 #pragma unroll
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(kNT, LEAN ? 3 : 2) tile_kernel(const __grid_co
         Dft<8, -1>::run(x);
         if (FWD_ONLY) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) P.Hout[tile_base + pos0 + q] = x[q];
+            for (int q = 0; q < 8; q++) P.Hout[tile_base + (q << 9) + hu] = x[q];
         } else {
 #pragma unroll
             for (int q = 0; q < 8; q++) x[q] = cmul(x[q], h[q]);

@@ -417,8 +417,34 @@ class ARTModel(InterpolationModel):
     """Atomic-Raman-tensor model (``ramannoodle/pmodel/_art.py:48``): evaluation is inherited
     unchanged; every DOF is one linear piece, so it runs through the affine kernel."""
 
+    def get_dof_indexes(self, atom_indexes_or_symbols) -> list:
+        """DOF indexes of certain atoms (``ramannoodle/pmodel/_art.py:335-365``): integers are atom
+        indexes, strings atom symbols (mixtures allowed).  A DOF belongs to an atom when its basis
+        vector moves that atom (``not np.allclose(direction, 0, atol=1e-5)``); the result keeps the
+        reference's order (atoms in ``set`` order, DOFs ascending) so that
+        ``get_masked_model(get_dof_indexes("Ti"))`` reads like the masking tutorial."""
+        if not isinstance(atom_indexes_or_symbols, list):
+            atom_indexes_or_symbols = [atom_indexes_or_symbols]
+        atom_indexes = []
+        for item in atom_indexes_or_symbols:
+            if isinstance(item, str):
+                atom_indexes += self._state.get_atom_indexes(item)
+            else:
+                atom_indexes += [item]
+        atom_indexes = list(set(atom_indexes))
+        if not self._state.basis_vectors:
+            return []
+        basis = np.stack([np.asarray(v, dtype=np.float64).reshape(self.num_atoms, 3) for v in self._state.basis_vectors])
+        moves = ~np.all(np.abs(basis) <= 1e-5, axis=2)  # (J,N): allclose(direction, 0, atol=1e-5, rtol irrelevant at 0)
+        dof_indexes = []
+        for atom_index in atom_indexes:
+            dof_indexes += [int(j) for j in np.nonzero(moves[:, atom_index])[0]]
+        return dof_indexes
+
 
 def accelerate(model, device: int | None = None, force_dense: bool = False) -> InterpolationModel:
-    """Wrap a reference ``InterpolationModel``/``ARTModel`` for GPU evaluation."""
+    """Wrap a reference ``InterpolationModel``/``ARTModel`` for GPU evaluation.  The state is
+    SNAPSHOTTED: later changes to the reference object (``add_dof``, ``mask = ...``) are not seen —
+    wrap again, or use ``ramannoodle_b200.install()``, which tracks the live object."""
     cls = ARTModel if type(model).__name__ == "ARTModel" else InterpolationModel
     return cls.from_reference(model, device=device, force_dense=force_dense)

@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .exceptions import verify_ndarray_shape
+from .exceptions import get_type_error, verify_ndarray_shape
 
 
 @dataclass
@@ -28,6 +28,7 @@ class ModelState:
     splines: list = field(default_factory=list)  # J x (t, c(n,3,3), k)
     mask: np.ndarray = field(default_factory=lambda: np.array([], dtype=bool))
     is_dummy_model: bool = False
+    atomic_numbers: list | None = None  # (N,) — only ARTModel.get_dof_indexes(symbol) needs them
 
     def __post_init__(self) -> None:
         self.ref_positions = np.ascontiguousarray(self.ref_positions, dtype=np.float64)
@@ -63,6 +64,7 @@ class ModelState:
                      for s in model._interpolations],
             mask=np.array(model._mask, dtype=bool),
             is_dummy_model=bool(getattr(model, "_is_dummy_model", False)),
+            atomic_numbers=[int(z) for z in getattr(structure, "atomic_numbers", [])] or None,
         )
 
     def add_dof(self, basis_vector, t, c, k) -> None:
@@ -108,3 +110,23 @@ class ModelState:
     def fingerprint(self) -> tuple:
         """Cheap change detector for the mutable parts (mask edits, added DOFs)."""
         return (self.num_dofs, len(self.splines), self.mask.tobytes())
+
+    def get_atom_indexes(self, atom_symbols) -> list:
+        """``ReferenceStructure.get_atom_indexes`` (``ramannoodle/structure/_reference.py:344-364``)."""
+        if self.atomic_numbers is None:
+            raise ValueError("this model state carries no atomic numbers (pass atomic_numbers=...)")
+        symbols = [ATOM_SYMBOLS[number] for number in self.atomic_numbers]
+        if isinstance(atom_symbols, str):
+            atom_symbols = [atom_symbols]
+        try:
+            return [index for index, symbol in enumerate(symbols) if symbol in atom_symbols]
+        except TypeError as err:
+            raise get_type_error("atom_symbols", atom_symbols, "list") from err
+
+
+# element symbols by atomic number (the periodic table; ramannoodle/constants.py:125-246 holds the same map)
+ATOM_SYMBOLS = dict(enumerate(
+    "H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr Rb Sr Y Zr "
+    "Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu Hf Ta W Re Os Ir "
+    "Pt Au Hg Tl Pb Bi Po At Rn Fr Ra Ac Th Pa U Np Pu Am Cm Bk Cf Es Fm Md No Lr Rf Db Sg Bh Hs Mt Ds Rg Cn Nh Fl "
+    "Mc Lv Ts Og".split(), start=1))

@@ -174,6 +174,15 @@ def frequency_of_position(log2lh: int) -> np.ndarray:
     return k
 
 
+def filter_layout(log2lh: int) -> np.ndarray:
+    """Where the kernels STORE position p of the forward transform (filter spectrum, rn_debug_fft_forward):
+    inside every 4096-element tile the eight outputs q of butterfly u (position 8u + q) sit at q * 512 + u,
+    so that consecutive threads read consecutive addresses."""
+    pos = np.arange(1 << log2lh)
+    inner = pos & (E - 1)
+    return (pos - inner) + ((inner & 7) << 9) + (inner >> 3)
+
+
 # ---- chirp-z on top ---------------------------------------------------------------------------
 SQ5, SQ525, SQ175, SQ21 = np.sqrt(5.0), np.sqrt(5.25), np.sqrt(1.75), np.sqrt(21.0)
 

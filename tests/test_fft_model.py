@@ -22,6 +22,13 @@ def test_forward_is_a_permuted_fft(log2lh):
     assert np.abs(y - ref[perm]).max() / np.abs(ref).max() < 1e-13
 
 
+def test_filter_layout_is_a_tilewise_permutation():
+    layout = fm.filter_layout(14)
+    assert sorted(layout.tolist()) == list(range(1 << 14))
+    assert np.array_equal(layout // fm.E, np.arange(1 << 14) // fm.E)
+    assert layout[8 * 5 + 3] == 3 * 512 + 5 and layout[fm.E + 8 * 511 + 7] == fm.E + 7 * 512 + 511
+
+
 def test_two_level_plan_forward():
     log2lh = 23  # 2^11 rows above the tiles -> levels of 2^6 and 2^5
     assert fm.plan_levels(log2lh) == [6, 5]

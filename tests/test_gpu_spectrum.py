@@ -182,7 +182,8 @@ def test_fft_forward_against_torch(log2l):
                                            stream) == 0
     ref = torch.fft.fft(torch.view_as_complex(x))
     perm = torch.from_numpy(fft_model.frequency_of_position(log2l)).to("cuda:0")
-    got = torch.view_as_complex(out)
+    stored = torch.from_numpy(fft_model.filter_layout(log2l)).to("cuda:0")
+    got = torch.view_as_complex(out)[stored]  # position p of the transform is stored at stored[p]
     err = float((got - ref[perm]).abs().max() / ref.abs().max())
     assert err < 1e-13, f"L=2^{log2l}: {err}"
 

@@ -1,27 +1,31 @@
-"""Top SASS instructions by warp-stall samples from `ncu --page source --csv --print-source sass`."""
+"""Hottest SASS lines of one kernel from an .ncu-rep:  python tools/ncu_hot.py REPORT KERNEL_REGEX [TOP]"""
 import csv
+import io
+import subprocess
 import sys
-import collections
 
-path = sys.argv[1]
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-rows = list(csv.reader(open(path)))
-# multiple kernels concatenated: take the first block
-hdr_idx = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
-start = hdr_idx[0]
-end = hdr_idx[1] - 1 if len(hdr_idx) > 1 else len(rows)
-hdr = rows[start]
-body = rows[start + 1:end]
-ci = {k: i for i, k in enumerate(hdr)}
-samples = [(int(r[ci['# Samples']] or 0), idx, r) for idx, r in enumerate(body) if len(r) > ci['# Samples']]
-total = sum(s for s, _, _ in samples)
-print('total samples', total, 'instructions', len(body))
-by_op = collections.Counter()
-for s, _, r in samples:
-    op = r[ci['Source']].split()[0] if r[ci['Source']].split() else '?'
-    if op.startswith('@'):
-        op = r[ci['Source']].split()[1]
-    by_op[op.split('.')[0]] += s
-print('by opcode:', [(k, round(100 * v / total, 1)) for k, v in by_op.most_common(14)])
-for s, idx, r in sorted(samples, reverse=True)[:top]:
-    print(f"{100*s/total:5.1f}%  #{idx:5d}  exec={r[ci['Instructions Executed']]:>9s}  {r[ci['Source']].strip()[:100]}")
+report, kernel = sys.argv[1], sys.argv[2]
+top_n = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+text = subprocess.run(["ncu", "-i", report, "--page", "source", "--csv", "--kernel-name", f"regex:{kernel}"],
+                      capture_output=True, text=True, check=False).stdout
+rows = list(csv.reader(io.StringIO(text)))
+blocks, current = [], None
+for row in rows:
+    if row and row[0] == "Kernel Name":
+        current = {"name": row[1], "rows": []}
+        blocks.append(current)
+    elif current is not None:
+        current["rows"].append(row)
+for block in blocks[:1]:
+    hdr = block["rows"][0]
+    ci, cs, cx = hdr.index("Source"), hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
+    data = []
+    for row in block["rows"][1:]:
+        try:
+            data.append((float(row[cs] or 0), row[cx], row[ci]))
+        except (ValueError, IndexError):
+            continue
+    total = sum(d[0] for d in data) or 1.0
+    print(block["name"], "samples", total, "sass lines", len(data))
+    for samples, executed, source in sorted(data, key=lambda d: -d[0])[:top_n]:
+        print(f"{samples / total * 100:5.1f}%  x{executed:>8}  {source[:110]}")

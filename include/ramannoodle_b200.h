@@ -186,7 +186,10 @@ int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, double timeste
  * The caller separates the steps with a cross-rank barrier (the buffers are peer-mapped device memory,
  * e.g. symmetric memory over NVLink) and provides, per rank, a work buffer, a receive buffer and a
  * power buffer of rn_spectrum_dist_sizes bytes.  All ranks of the world call every step; for spectator
- * ranks (rank >= G) steps 2-4 return immediately. */
+ * ranks (rank >= G) steps 2-4 return immediately.  Steps 2 and 3 take `seq`: -1 handles the three packed
+ * sequences in one go; 0, 1, 2 handle one sequence, so that a caller can pipeline them on several
+ * streams (the NVLink-bound stores of one sequence overlap the transform of another; the pass with
+ * seq = 0 also sums the series energies, and must be among the passes). */
 int rn_spectrum_plan_create_dist(int64_t num_frames, int device, int world, int rank,
                                  rn_spectrum_plan** out);
 /* info[0]=log2 L, [1]=ranks sharing the transform, [2]=log2 of the local length, [3]=strided levels,
@@ -196,9 +199,9 @@ int rn_spectrum_dist_sizes(const rn_spectrum_plan* plan, int64_t* work_bytes, in
                            int64_t* power_bytes);
 int rn_spectrum_dist_route(const rn_spectrum_plan* plan, int64_t* period, int64_t* width);
 int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_series, double* const* peer_work,
-                          void* stream);
+                          int seq, void* stream);
 int rn_spectrum_dist_transform(rn_spectrum_plan* plan, double* d_work, double* const* peer_recv,
-                               void* stream);
+                               int seq, void* stream);
 int rn_spectrum_dist_final(rn_spectrum_plan* plan, const double* d_recv, double* const* dest_power,
                            int num_dest, void* stream);
 int rn_spectrum_dist_combine(const rn_spectrum_plan* plan, const double* d_power, double timestep_fs,
@@ -242,6 +245,16 @@ int rn_outcar_scan(const char* path, int64_t* num_frames, int64_t* num_atoms, do
                    double* timestep_fs);
 int rn_outcar_read(const char* path, double* h_positions, int64_t num_frames, int64_t num_atoms,
                    const double* inv_lattice, int num_threads, int wrap);
+
+/* vasprun.xml molecular-dynamics trajectories (ramannoodle/io/vasp/vasprun.py:298-330, _parse_positions
+ * :53-70, _parse_timestep :281-295): every unnamed `structure` element directly under the root is a frame
+ * (rows of its first `varray`), POTIM is the timestep.  Host-only, same pattern as the XDATCAR reader:
+ * scan (frame / atom counts, timestep in fs), then read into a (num_frames, num_atoms, 3) buffer.
+ * RN_ERR_INVALID_ARGUMENT: what the reference reports as InvalidFileException; RN_ERR_UNSUPPORTED: markup
+ * the tokenizer does not handle — the caller re-reads the file with a full XML parser. */
+int rn_vasprun_scan(const char* path, int64_t* num_frames, int64_t* num_atoms, double* timestep_fs);
+int rn_vasprun_read(const char* path, double* h_positions, int64_t num_frames, int64_t num_atoms,
+                    int num_threads, int wrap);
 
 /* Host-side Trajectory.__init__ wrap (dynamics/_trajectory.py:45; structure/utils.py:27:
  * positions - positions // 1) with a thread pool: h_out[i] = h_in[i] - floor(h_in[i]), identical to

@@ -10,6 +10,7 @@ Writes
   tests/golden/smearing.npz              the reference's own known_{gaussian,lorentzian}_spectrum goldens
   tests/golden/phonons_tio2.npz          Phonons.get_raman_spectrum / PhononRamanSpectrum.measure (next row N1)
   tests/golden/sto_xdatcar*.{txt,npz}    the reference's XDATCAR fixture + its read_positions_ts output (next row N2)
+  tests/golden/tio2_md_run_vasprun.*     the reference's vasprun.xml MD fixture + its read_trajectory output (N2)
 Everything here is produced by importing the reference through ``oracle/ref_bootstrap.py``
 (spglib/defusedxml stubbed; hot-path arithmetic untouched).  The GPU box has no reference
 tree: tests there read only these files.
@@ -246,6 +247,25 @@ def make_ingest() -> None:
                         timestep=trajectory.timestep)
 
 
+def make_vasprun() -> None:
+    """Next row N2, vasprun.xml: the reference's molecular-dynamics fixture
+    (``test/data/TiO2/md_run_vasprun.xml``, 19 frames x 108 atoms, POTIM 1 fs; pinned by
+    ``test/tests/test_vasprun.py:102-126``), gzip-compressed DATA copy, and what the reference reader
+    (``io/vasp/vasprun.py:298-330``, running on the standard library's ElementTree) makes of it."""
+    import gzip
+    import shutil
+
+    from ramannoodle.io.vasp.vasprun import read_trajectory
+
+    src = os.path.join(REFERENCE_ROOT, "test/data/TiO2/md_run_vasprun.xml")
+    with open(src, "rb") as fin, gzip.GzipFile(os.path.join(GOLDEN, "tio2_md_run_vasprun.xml.gz"), "wb",
+                                               mtime=0) as fout:
+        shutil.copyfileobj(fin, fout)
+    trajectory = read_trajectory(src)
+    np.savez_compressed(os.path.join(GOLDEN, "tio2_md_run_vasprun.npz"), positions_ts=trajectory.positions_ts,
+                        timestep=trajectory.timestep)
+
+
 def make_smearing() -> None:
     """The reference's own goldens for ``convolve_spectrum``
     (``test/tests/test_phonon_spectrum.py:403-449``)."""
@@ -268,6 +288,7 @@ def main() -> None:
     make_spectrum()
     make_phonons()
     make_ingest()
+    make_vasprun()
     for path in sorted(glob.glob(os.path.join(GOLDEN, "*.npz")) + glob.glob(os.path.join(DATA, "*.npz"))):
         print(f"{os.path.getsize(path):>9d}  {os.path.relpath(path, REPO)}")
 

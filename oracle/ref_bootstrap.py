@@ -8,7 +8,8 @@ oracle restatement against the real reference when the reference tree is present
 The reference eagerly imports every sub-package (``ramannoodle/__init__.py:4-12``) and two
 of its dependencies are not installed here (``spglib`` used at
 ``ramannoodle/structure/_reference.py:114-122``; ``defusedxml`` used only by
-``ramannoodle/io/vasp/vasprun.py``).  We inject in-memory stubs for both.  The spglib stub
+``ramannoodle/io/vasp/vasprun.py``).  We inject in-memory stand-ins for both (``defusedxml.ElementTree``
+is the standard library's ``xml.etree.ElementTree``, whose API it mirrors).  The spglib stub
 reports the identity operation only ("P1"): the MD-Raman hot path
 (``calc_polarizabilities`` / ``Trajectory`` / ``measure`` / ``convolve_spectrum``) never
 touches symmetry, so the hot-path arithmetic that runs is exactly the reference's.
@@ -43,10 +44,14 @@ def import_reference():
 
         sp.get_symmetry = get_symmetry
         sys.modules["spglib"] = sp
-    for name in ("defusedxml", "defusedxml.ElementTree"):
-        if name not in sys.modules:
-            sys.modules[name] = types.ModuleType(name)
-    sys.modules["defusedxml"].ElementTree = sys.modules["defusedxml.ElementTree"]
+    if "defusedxml" not in sys.modules:
+        # defusedxml.ElementTree has the API of the standard library's ElementTree (it only refuses a few
+        # dangerous constructs): the stdlib module stands in, so the vasprun.xml readers run too
+        import xml.etree.ElementTree as stdlib_etree  # pylint: disable=import-outside-toplevel
+
+        sys.modules["defusedxml"] = types.ModuleType("defusedxml")
+        sys.modules["defusedxml.ElementTree"] = stdlib_etree
+        sys.modules["defusedxml"].ElementTree = stdlib_etree
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import ramannoodle  # noqa: E402  pylint: disable=import-outside-toplevel

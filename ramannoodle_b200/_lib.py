@@ -60,8 +60,10 @@ PROTOTYPES = {
     "rn_spectrum_plan_info": (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
     "rn_spectrum_dist_sizes": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, c_int64_p, c_int64_p]),
     "rn_spectrum_dist_route": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, c_int64_p]),
-    "rn_spectrum_dist_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "rn_spectrum_dist_transform": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "rn_spectrum_dist_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.c_void_p]),
+    "rn_spectrum_dist_transform": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                  ctypes.c_void_p]),
     "rn_spectrum_dist_final": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                               ctypes.c_void_p]),
     "rn_spectrum_dist_combine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
@@ -83,6 +85,9 @@ PROTOTYPES = {
     "rn_outcar_scan": (ctypes.c_int, [ctypes.c_char_p, c_int64_p, c_int64_p, ctypes.c_void_p, ctypes.c_void_p]),
     "rn_outcar_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "rn_vasprun_scan": (ctypes.c_int, [ctypes.c_char_p, c_int64_p, c_int64_p, c_double_p]),
+    "rn_vasprun_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_int, ctypes.c_int]),
     "rn_host_apply_pbc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     "rn_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     "rn_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),

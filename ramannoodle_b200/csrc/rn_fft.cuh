@@ -231,6 +231,7 @@ struct TileParams {
     const double2* H;      // (seq_stride) filter spectrum in the transform's digit-reversed order
     double2* Hout;         // FWD_ONLY: forward transform written here (plan creation)
     int64_t limit;         // input elements with index >= limit (within the sequence) read as zero
+    int seq_base;          // number of the first sequence in X (names the slot in OUT_POWER / OUT_PEERS)
     OutSpec out;
     Twiddles tw;
 };
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(kNT, LEAN ? 3 : 2) tile_kernel(const __grid_co
     __syncthreads();
     fft_stage<+1, 8, LEAN>(6, 0, wsub, rd_s, wr_s);
     __syncthreads();
-    auto wr_g = [&](int pos, int, double2 v) { store_out(P.out, base + pos, seq, tile_base + pos, v); };
+    auto wr_g = [&](int pos, int, double2 v) { store_out(P.out, base + pos, P.seq_base + seq, tile_base + pos, v); };
     fft_stage<+1, 8, LEAN>(9, 0, wsub, rd_s, wr_g);
 }
 
@@ -308,6 +309,7 @@ struct LevelParams {
     int nsub;
     int tw_shift;     // W_Lsub^e = W_L^(e << tw_shift)
     int64_t limit;    // forward: input elements with index >= limit (within the sequence) read as zero
+    int seq_base;     // number of the first sequence in X (names the slot in OUT_POWER / OUT_PEERS)
     OutSpec out;      // inverse: where the result goes
     Twiddles tw;
 };
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(kNT, LEAN ? 3 : 2) level_kernel(const __grid_c
     const double2* wsub = P.tw.sub;
     const int a8 = P.log2r / 3, r1 = P.log2r % 3;
     const int B = 1 << log2b;
-    LevelCtx<SGN> C{P, S, base, elem_base, seq, log2b, log2s, a8, chunk << log2b};
+    LevelCtx<SGN> C{P, S, base, elem_base, P.seq_base + seq, log2b, log2s, a8, chunk << log2b};
 
     auto rd_s = [&](int pos, int) { return S[swz(pos)]; };
     auto wr_s = [&](int pos, int, double2 v) { S[swz(pos)] = v; };
@@ -459,7 +461,7 @@ __global__ void __launch_bounds__(kNT, LEAN ? 3 : 2) level_kernel(const __grid_c
         }
         auto wr_g = [&](int pos, int, double2 v) {
             const int64_t off = goff(pos);
-            store_out(P.out, base + off, seq, elem_base + off, v);
+            store_out(P.out, base + off, P.seq_base + seq, elem_base + off, v);
         };
         fft_stage<+1, 8, LEAN>(kLog2E - 3, log2b, wsub, rd_s, wr_g);
     }

@@ -92,6 +92,7 @@ struct PackParams {
     int64_t begin, end;  // this rank's block of n'
     double2* dst[8];     // work buffers of ranks 0..G-1 (nseq, Lh); G == 1: the local one
     int aligned16;         // src is 16-byte aligned (vector loads)
+    int seq_sel;           // -1: pack all three sequences; 0..2: only this one (0 also sums the energies)
     double* epart;         // [blocks] partials, then their sum
     unsigned int* ticket;  // zero between launches
     Twiddles tw;
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_alpha_kernel(const __grid_c
             const double2 w1 = fft::tw_global(P.tw, (uint32_t)n1);  // W_L^{n'}
 #pragma unroll
             for (int s = 0; s < 3; s++) {
+                if (P.seq_sel >= 0 && s != P.seq_sel) continue;
                 double2 x[G];
 #pragma unroll
                 for (int q = 0; q < G; q++) x[q] = q < GH ? a[q < GH ? q : 0][s] : make_double2(0.0, 0.0);
@@ -214,8 +216,10 @@ __global__ void __launch_bounds__(kPackThreads) pack_alpha_kernel(const __grid_c
             }
         }
     }
-    const double total = block_sum(energy, red);
-    publish_energy(total, P.epart, P.ticket, red);
+    if (P.seq_sel <= 0) {  // uniform over the grid
+        const double total = block_sum(energy, red);
+        publish_energy(total, P.epart, P.ticket, red);
+    }
 }
 
 // one real signal (calc_signal_spectrum): z = x, chirp pre-multiply
@@ -418,10 +422,11 @@ static fft::OutSpec plain_out() {
 }
 
 template <int SGN>
-static int launch_level(const rn_spectrum_plan* p, double2* X, int nseq, int lev, int64_t limit,
+static int launch_level(const rn_spectrum_plan* p, double2* X, int nseq, int seq_base, int lev, int64_t limit,
                         const fft::OutSpec& out, cudaStream_t stream) {
     fft::LevelParams P;
     P.X = X;
+    P.seq_base = seq_base;
     P.seq_stride = p->Lh;
     int log2lsub = p->log2lh;
     for (int i = 0; i < lev; i++) log2lsub -= p->lev_log2r[i];
@@ -444,12 +449,12 @@ static int launch_level(const rn_spectrum_plan* p, double2* X, int nseq, int lev
 // elements at or beyond it are zero (never read); `out`: where the inverse transform's result goes.
 // hout != nullptr: forward transform only, written to hout (plan creation: the filter spectrum).
 static int run_convolution(const rn_spectrum_plan* p, double2* X, int nseq, int64_t limit, const fft::OutSpec& out,
-                           double2* hout, cudaStream_t stream) {
+                           double2* hout, cudaStream_t stream, int seq_base = 0) {
     int rc = ensure_smem_attr(p->device);
     if (rc != RN_OK) return rc;
     const fft::OutSpec plain = plain_out();
     for (int lev = 0; lev < p->nlev; lev++) {
-        rc = launch_level<-1>(p, X, nseq, lev, lev == 0 ? limit : p->Lh, plain, stream);
+        rc = launch_level<-1>(p, X, nseq, seq_base, lev, lev == 0 ? limit : p->Lh, plain, stream);
         if (rc != RN_OK) return rc;
     }
     fft::TileParams T;
@@ -459,6 +464,7 @@ static int run_convolution(const rn_spectrum_plan* p, double2* X, int nseq, int6
     T.H = p->d_H;
     T.Hout = hout;
     T.limit = p->nlev == 0 ? limit : p->Lh;
+    T.seq_base = seq_base;
     T.out = p->nlev == 0 ? out : plain;
     T.tw = plan_twiddles(p);
     const unsigned grid = (unsigned)((int64_t)nseq * T.tiles_per_seq);
@@ -469,7 +475,7 @@ static int run_convolution(const rn_spectrum_plan* p, double2* X, int nseq, int6
     RN_CUDA(cudaGetLastError());
     if (hout) return RN_OK;
     for (int lev = p->nlev - 1; lev >= 0; lev--) {
-        rc = launch_level<+1>(p, X, nseq, lev, p->Lh, lev == 0 ? out : plain, stream);
+        rc = launch_level<+1>(p, X, nseq, seq_base, lev, p->Lh, lev == 0 ? out : plain, stream);
         if (rc != RN_OK) return rc;
     }
     return RN_OK;
@@ -678,6 +684,7 @@ extern "C" int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, dou
     for (int i = 0; i < 8; i++) pp.dst[i] = nullptr;
     pp.dst[0] = plan->d_work;
     pp.aligned16 = (reinterpret_cast<uintptr_t>(pp.src) % 16 == 0) ? 1 : 0;
+    pp.seq_sel = -1;
     pp.epart = plan->d_epart;
     pp.ticket = plan->d_ticket;
     pp.tw = plan_twiddles(plan);
@@ -718,6 +725,7 @@ extern "C" int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal
     for (int i = 0; i < 8; i++) pp.dst[i] = nullptr;
     pp.dst[0] = plan->d_work;
     pp.aligned16 = (reinterpret_cast<uintptr_t>(pp.src) % 16 == 0) ? 1 : 0;
+    pp.seq_sel = -1;
     pp.epart = plan->d_epart;
     pp.ticket = plan->d_ticket;
     pp.tw = plan_twiddles(plan);
@@ -765,8 +773,9 @@ static int launch_pack_dist(const rn_spectrum_plan* plan, const PackParams& pp, 
 }
 
 extern "C" int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_series, double* const* peer_work,
-                                     void* stream) {
+                                     int seq, void* stream) {
     RN_CHECK_ARG(plan && d_series && peer_work, "null pointer");
+    RN_CHECK_ARG(seq >= -1 && seq <= 2, "seq must be -1 (all) or 0..2");
     if (plan->rank >= plan->world) return RN_OK;  // spectator
     RN_CHECK_ARG(plan->world > 1, "rn_spectrum_dist_pack needs a plan from rn_spectrum_plan_create_dist with world > 1");
     DeviceGuard guard(plan->device);
@@ -783,9 +792,11 @@ extern "C" int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_ser
         pp.dst[r] = reinterpret_cast<double2*>(peer_work[r]);
     }
     pp.aligned16 = (reinterpret_cast<uintptr_t>(pp.src) % 16 == 0) ? 1 : 0;
+    pp.seq_sel = -1;
     pp.epart = plan->d_epart;
     pp.ticket = plan->d_ticket;
     pp.tw = plan_twiddles(plan);
+    pp.seq_sel = seq;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (plan->world == 2) return launch_pack_dist<2>(plan, pp, s);
     if (plan->world == 4) return launch_pack_dist<4>(plan, pp, s);
@@ -793,8 +804,9 @@ extern "C" int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_ser
 }
 
 extern "C" int rn_spectrum_dist_transform(rn_spectrum_plan* plan, double* d_work, double* const* peer_recv,
-                                          void* stream) {
+                                          int seq, void* stream) {
     RN_CHECK_ARG(plan && d_work && peer_recv, "null pointer");
+    RN_CHECK_ARG(seq >= -1 && seq <= 2, "seq must be -1 (all) or 0..2");
     if (plan->rank >= plan->world) return RN_OK;
     RN_CHECK_ARG(plan->world > 1, "rn_spectrum_dist_transform needs a shared plan (world > 1)");
     DeviceGuard guard(plan->device);
@@ -809,8 +821,10 @@ extern "C" int rn_spectrum_dist_transform(rn_spectrum_plan* plan, double* d_work
         RN_CHECK_ARG(peer_recv[r] != nullptr, "null receive buffer pointer for rank %d", r);
         out.peers.ptr[r] = reinterpret_cast<double2*>(peer_recv[r]);
     }
-    return run_convolution(plan, reinterpret_cast<double2*>(d_work), 3, plan->Lh, out, nullptr,
-                           static_cast<cudaStream_t>(stream));
+    double2* work = reinterpret_cast<double2*>(d_work);
+    if (seq < 0) return run_convolution(plan, work, 3, plan->Lh, out, nullptr, static_cast<cudaStream_t>(stream));
+    return run_convolution(plan, work + (int64_t)seq * plan->Lh, 1, plan->Lh, out, nullptr,
+                           static_cast<cudaStream_t>(stream), seq);
 }
 
 template <int G>

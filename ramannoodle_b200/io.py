@@ -2,13 +2,16 @@
 (``ramannoodle/io/generic.py: read_trajectory``):
 
 * XDATCAR: ``ramannoodle/io/vasp/xdatcar.py:21-81`` (``read_positions_ts`` / ``read_trajectory``),
-* OUTCAR molecular dynamics: ``ramannoodle/io/vasp/outcar.py:497-538``.
+* OUTCAR molecular dynamics: ``ramannoodle/io/vasp/outcar.py:497-538``,
+* vasprun.xml molecular dynamics: ``ramannoodle/io/vasp/vasprun.py:298-330``.
 
 The text is parsed by the native library (mmap + a pool of threads running a correctly rounded
 decimal parser, so every value equals Python's ``float(token)``), straight into the caller's buffer
 (page-locked when ``read_trajectory`` runs on a GPU box, so the ``Trajectory`` streams to the device
-at full PCIe bandwidth).  Only direct-coordinate XDATCAR frames are handled; vasprun.xml
-trajectories are not covered — use the reference's reader for those.
+at full PCIe bandwidth).  Only direct-coordinate XDATCAR frames are handled (Cartesian frames raise
+``InvalidFileException``; the reference converts them, ``poscar.py:118-119``).  vasprun.xml files the
+native tokenizer does not understand are re-read with the standard library's ElementTree under the
+reference's rules.
 """
 from __future__ import annotations
 
@@ -114,12 +117,66 @@ def read_outcar_positions_ts(filepath, num_threads: int = 0, out: np.ndarray | N
     return out, lattice, timestep
 
 
+def _vasprun_positions_etree(path: str):
+    """The reference's rules (``vasprun.py:53-70,281-330``) on a standard-library ElementTree: the
+    fallback for files the native tokenizer leaves alone, and its cross-check in the tests."""
+    import xml.etree.ElementTree as ET  # pylint: disable=import-outside-toplevel
+
+    try:
+        root = ET.parse(path).getroot()
+    except ET.ParseError as exc:
+        raise InvalidFileException("root xml element could not be found") from exc
+    positions_ts = []
+    for structure in root.iterfind("structure"):
+        if "name" in structure.attrib:  # skip named structures
+            continue
+        varray = structure.find("varray")
+        if varray is None:
+            raise InvalidFileException("structure varray not found")
+        rows = []
+        for child in varray:
+            if child.text is None:
+                raise InvalidFileException("varray child text not found")
+            rows.append([float(token) for token in child.text.split()])
+        positions_ts.append(np.array(rows))
+    if len(positions_ts) == 0:
+        raise InvalidFileException("no trajectory found")
+    element = root.find("./parameters/separator[@name='ionic']/i/[@name='POTIM']")
+    if element is None:
+        raise InvalidFileException("timestep not found")
+    if element.text is None:
+        raise InvalidFileException("potim element has no text")
+    return np.array(positions_ts), float(element.text.strip())
+
+
+def read_vasprun_positions_ts(filepath, num_threads: int = 0, out: np.ndarray | None = None, wrap: bool = False):
+    """``(positions_ts, timestep)`` of a vasprun.xml molecular-dynamics run: the unnamed root-level
+    ``structure`` elements are the frames, POTIM is the timestep (``vasprun.py:298-330``)."""
+    path = _checked_path(filepath)
+    frames, atoms, timestep = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+    status = _lib.lib().rn_vasprun_scan(path.encode(), ctypes.byref(frames), ctypes.byref(atoms), ctypes.byref(timestep))
+    if status == 0:
+        out = _output(out, int(frames.value), int(atoms.value))
+        status = _lib.lib().rn_vasprun_read(path.encode(), ctypes.c_void_p(out.ctypes.data), int(frames.value),
+                                            int(atoms.value), num_threads, int(bool(wrap)))
+        if status == 0:
+            return out, float(timestep.value)
+    if status == -1:
+        raise InvalidFileException(_lib.last_error())
+    # RN_ERR_UNSUPPORTED (irregular markup / rows) or anything else: the ElementTree walk decides
+    positions, file_timestep = _vasprun_positions_etree(path)
+    if wrap:
+        positions = positions - positions // 1
+    return positions, file_timestep
+
+
 def read_trajectory(filepath, timestep: float | None = None, file_format: str = "xdatcar",
                     num_threads: int = 0) -> Trajectory:
     """``Trajectory`` from a trajectory file (``ramannoodle/io/generic.py: read_trajectory``).
 
     ``file_format="xdatcar"`` needs ``timestep`` (fs; XDATCAR files do not store it,
-    ``xdatcar.py:59-81``); ``"outcar"`` reads it from the file (``outcar.py:481-494``) unless given.
+    ``xdatcar.py:59-81``); ``"outcar"`` and ``"vasprun.xml"`` read it from the file (``outcar.py:481-494``,
+    ``vasprun.py:281-295``) unless given.
     The text is parsed straight into the (pinned) buffer the ``Trajectory`` owns."""
     path = _checked_path(filepath)
     if file_format == "xdatcar":
@@ -134,6 +191,17 @@ def read_trajectory(filepath, timestep: float | None = None, file_format: str = 
         positions, _, _ = read_outcar_positions_ts(path, num_threads=num_threads, out=out, wrap=True)
         if timestep is None:
             timestep = file_timestep
+    elif file_format in ("vasprun.xml", "vasprun"):
+        frames, atoms, file_timestep = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+        owner = out = None
+        if _lib.lib().rn_vasprun_scan(path.encode(), ctypes.byref(frames), ctypes.byref(atoms),
+                                      ctypes.byref(file_timestep)) == 0:
+            owner, out = _pinned(int(frames.value), int(atoms.value))
+        positions, parsed_timestep = read_vasprun_positions_ts(path, num_threads=num_threads, out=out, wrap=True)
+        if positions is not out:
+            return Trajectory(positions, parsed_timestep if timestep is None else timestep)
+        if timestep is None:
+            timestep = parsed_timestep
     else:
         raise ValueError(f"unsupported format: {file_format}")
     return Trajectory._from_wrapped(positions, timestep, owner)  # pylint: disable=protected-access

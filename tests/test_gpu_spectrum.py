@@ -212,7 +212,7 @@ def test_fft_convolve_against_torch(log2l):
     assert err < 1e-12, f"L=2^{log2l}: {err}"
 
 
-def _emulated_shared_measure(alpha, timestep, world, **corrections):
+def _emulated_shared_measure(alpha, timestep, world, by_sequence=False, **corrections):
     """The multi-GPU measure (rn_spectrum_dist_*: one transform shared by `world` ranks) with every
     rank emulated on cuda:0 — the same kernels and buffers, peers being local pointers."""
     import ctypes
@@ -241,11 +241,14 @@ def _emulated_shared_measure(alpha, timestep, world, **corrections):
         def table(tensors):
             return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
-        for rank in range(world):
-            assert lib.rn_spectrum_dist_pack(plans[rank], ctypes.c_void_p(d_alpha.data_ptr()), table(work[:group]), stream) == 0
-        for rank in range(world):
-            assert lib.rn_spectrum_dist_transform(plans[rank], ctypes.c_void_p(work[rank].data_ptr()), table(recv[:group]),
-                                                  stream) == 0
+        # all three sequences in one launch, or one sequence per launch (what the pipelined schedule does)
+        for seq in ((-1,) if not by_sequence else (2, 0, 1)):
+            for rank in range(world):
+                assert lib.rn_spectrum_dist_pack(plans[rank], ctypes.c_void_p(d_alpha.data_ptr()), table(work[:group]),
+                                                 seq, stream) == 0
+            for rank in range(world):
+                assert lib.rn_spectrum_dist_transform(plans[rank], ctypes.c_void_p(work[rank].data_ptr()),
+                                                      table(recv[:group]), seq, stream) == 0
         for rank in range(world):
             assert lib.rn_spectrum_dist_final(plans[rank], ctypes.c_void_p(recv[rank].data_ptr()), table(power), world,
                                               stream) == 0
@@ -277,7 +280,8 @@ def test_shared_transform_matches_measure(frames, world):
              + 0.01 * rng.normal(size=(frames, 3, 3)))
     ref_wn, ref_inten = ora.md_measure(alpha, 1.5, laser_correction=True, laser_wavelength=532,
                                        bose_einstein_correction=True, temperature=250)
-    results = _emulated_shared_measure(alpha, 1.5, world, laser_wavelength=532, temperature=250)
+    results = _emulated_shared_measure(alpha, 1.5, world, by_sequence=(frames % 2 == 0), laser_wavelength=532,
+                                       temperature=250)
     single = rb.MDRamanSpectrum(alpha, 1.5).measure(laser_correction=True, laser_wavelength=532,
                                                     bose_einstein_correction=True, temperature=250)[1]
     for wn, inten in results:

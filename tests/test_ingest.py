@@ -115,7 +115,7 @@ def test_malformed_files(tmp_path):
     with pytest.raises(FileNotFoundError):
         rio.read_positions_ts(tmp_path / "missing")
     with pytest.raises(ValueError, match="unsupported format"):
-        rio.read_trajectory(good, 1.0, file_format="vasprun.xml")
+        rio.read_trajectory(good, 1.0, file_format="poscar")
     with pytest.raises(ValueError, match="timestep is required"):
         rio.read_trajectory(good)
 
@@ -325,3 +325,130 @@ def test_parallel_frame_scan_keeps_reference_semantics(tmp_path):
     write(tmp_path / "truncated", tail="Direct configuration=   801\n  0.1 0.2 0.3\n")
     with pytest.raises(rio.InvalidFileException, match="file ends inside frame 801"):
         rio.read_positions_ts(tmp_path / "truncated")
+
+
+def _vasprun_fixture(tmp_path):
+    import gzip
+    import shutil
+
+    path = tmp_path / "md_run_vasprun.xml"
+    with gzip.open(os.path.join(GOLDEN, "tio2_md_run_vasprun.xml.gz"), "rb") as fin, open(path, "wb") as fout:
+        shutil.copyfileobj(fin, fout)
+    return path
+
+
+def test_vasprun_reference_fixture_bit_identical(tmp_path):
+    """``test/tests/test_vasprun.py:102-126`` (19 frames, last position, POTIM 1 fs) and, beyond that pin,
+    the whole array the reference reader (``io/vasp/vasprun.py:298-330``, run on the standard library's
+    ElementTree by ``oracle/make_golden.py``) returns for its molecular-dynamics fixture."""
+    path = _vasprun_fixture(tmp_path)
+    known = np.load(os.path.join(GOLDEN, "tio2_md_run_vasprun.npz"))
+    for threads in (1, 4):
+        positions, timestep = rio.read_vasprun_positions_ts(path, num_threads=threads)
+        assert positions.shape == (19, 108, 3)
+        assert timestep == 1.0
+        assert np.allclose(positions[-1][-1], [0.83414850, 0.82850374, 0.30051845])
+        raw = positions - positions // 1  # the golden holds Trajectory.positions_ts (wrapped)
+        assert np.array_equal(raw, known["positions_ts"])
+    etree_positions, etree_timestep = rio._vasprun_positions_etree(str(path))  # pylint: disable=protected-access
+    assert np.array_equal(etree_positions, positions) and etree_timestep == timestep
+    trajectory = rio.read_trajectory(path, file_format="vasprun.xml")
+    assert len(trajectory) == 19 and trajectory.timestep == float(known["timestep"])
+    assert np.array_equal(np.asarray(trajectory.positions_ts), known["positions_ts"])
+    assert rio.read_trajectory(path, timestep=2.5, file_format="vasprun.xml").timestep == 2.5
+
+
+_VASPRUN_HEAD = """<?xml version="1.0" encoding="ISO-8859-1"?>
+<!-- synthetic -->
+<modeling>
+ <generator><i name="program" type="string">vasp </i></generator>
+ <parameters>
+  <separator name="electronic"><i name="POTIM">  9.0</i></separator>
+  <separator name="ionic">
+   <i type="int" name="NSW">     3</i>
+   <i name="POTIM">      {potim}</i>
+  </separator>
+ </parameters>
+ <structure name="initialpos">
+  <crystal><varray name="basis"><v> 4.0 0.0 0.0 </v><v> 0.0 4.0 0.0 </v><v> 0.0 0.0 4.0 </v></varray></crystal>
+  <varray name="positions"><v> 0.0 0.0 0.0 </v><v> 0.5 0.5 0.5 </v></varray>
+ </structure>
+"""
+
+
+def _vasprun_text(frames, potim="1.50000000", tail=""):
+    body = [_VASPRUN_HEAD.format(potim=potim)]
+    for frame in frames:
+        rows = "\n".join("   <v> " + " ".join(repr(float(x)) for x in row) + " </v>" for row in frame)
+        body.append(" <calculation><scstep><energy><i name='e_fr_energy'> -1.0 </i></energy></scstep>\n"
+                    "  <structure><crystal><varray name=\"basis\"><v> 4.0 0.0 0.0 </v><v> 0.0 4.0 0.0 </v>"
+                    "<v> 0.0 0.0 4.0 </v></varray></crystal><varray name=\"positions\" >\n" + rows +
+                    "\n  </varray></structure></calculation>\n")
+    for frame in frames:  # the frames ramannoodle reads: unnamed structures directly under the root
+        rows = "\n".join("   <v> " + " ".join(repr(float(x)) for x in row) + " </v>" for row in frame)
+        body.append(" <structure>\n  <crystal>\n   <varray name=\"basis\" >\n    <v> 4.0 0.0 0.0 </v>\n    <v> 0.0 4.0 0.0 </v>\n"
+                    "    <v> 0.0 0.0 4.0 </v>\n   </varray>\n  </crystal>\n  <varray name=\"positions\" >\n" + rows +
+                    "\n  </varray>\n  <varray name=\"velocities\"><v> 9.0 9.0 9.0 </v></varray>\n </structure>\n")
+    body.append(" <structure name=\"finalpos\"><varray name=\"positions\"><v> 0.1 0.1 0.1 </v></varray></structure>\n")
+    body.append(tail + "</modeling>\n")
+    return "".join(body)
+
+
+def test_vasprun_synthetic_against_etree_rules(tmp_path):
+    """A synthesised vasprun.xml (nested calculation structures, named structures, a second varray per
+    frame, a decoy POTIM, comments) through the native tokenizer against the ElementTree walk that
+    restates the reference's rules; values compare bit for bit with Python's float()."""
+    rng = np.random.default_rng(5)
+    frames = rng.uniform(-1.5, 2.5, size=(37, 11, 3))
+    frames[3, 2] = [1e-20, -0.0, 123456789.123456789]
+    path = tmp_path / "vasprun.xml"
+    path.write_text(_vasprun_text(frames))
+    etree_positions, etree_timestep = rio._vasprun_positions_etree(str(path))  # pylint: disable=protected-access
+    assert etree_positions.shape == (37, 11, 3) and etree_timestep == 1.5
+    assert np.array_equal(etree_positions, frames)
+    for threads in (1, 3):
+        positions, timestep = rio.read_vasprun_positions_ts(path, num_threads=threads)
+        assert np.array_equal(positions, frames) and timestep == 1.5
+    wrapped, _ = rio.read_vasprun_positions_ts(path, wrap=True)
+    assert np.array_equal(wrapped, frames - frames // 1)
+    # a larger file exercises the threaded row conversion
+    big = rng.uniform(0.0, 1.0, size=(400, 64, 3))
+    path.write_text(_vasprun_text(big, potim="0.5"))
+    positions, timestep = rio.read_vasprun_positions_ts(path)
+    assert np.array_equal(positions, big) and timestep == 0.5
+
+
+def test_vasprun_error_behaviour(tmp_path):
+    """``test/tests/test_vasprun.py:155-205``: a file that is not XML -> "root xml element could not be
+    found"; no unnamed root-level structure -> "no trajectory found"; plus the reader's other checks."""
+    frames = np.zeros((2, 2, 3))
+    not_xml = tmp_path / "POSCAR"
+    not_xml.write_text("TiO2\n 1.0\n 4.0 0.0 0.0\n")
+    with pytest.raises(rio.InvalidFileException, match="root xml element could not be found"):
+        rio.read_vasprun_positions_ts(not_xml)
+    empty = tmp_path / "empty.xml"
+    empty.write_text(_vasprun_text(frames[:0]))
+    with pytest.raises(rio.InvalidFileException, match="no trajectory found"):
+        rio.read_vasprun_positions_ts(empty)
+    with pytest.raises(rio.InvalidFileException, match="no trajectory found"):
+        rio.read_trajectory(empty, file_format="vasprun.xml")
+    no_potim = tmp_path / "no_potim.xml"
+    no_potim.write_text(_vasprun_text(frames).replace('name="POTIM">      1.5', 'name="TEBEG">      1.5'))
+    with pytest.raises(rio.InvalidFileException, match="timestep not found"):
+        rio.read_vasprun_positions_ts(no_potim)
+    no_varray = tmp_path / "no_varray.xml"
+    no_varray.write_text(_vasprun_text(frames, tail=" <structure><crystal></crystal></structure>\n"))
+    with pytest.raises(rio.InvalidFileException, match="structure varray not found"):
+        rio.read_vasprun_positions_ts(no_varray)
+    truncated = tmp_path / "truncated.xml"
+    truncated.write_text(_vasprun_text(frames)[:-30])
+    with pytest.raises(rio.InvalidFileException, match="root xml element could not be found"):
+        rio.read_vasprun_positions_ts(truncated)
+    with pytest.raises(FileNotFoundError):
+        rio.read_vasprun_positions_ts(tmp_path / "missing.xml")
+    # markup the tokenizer leaves to ElementTree: an entity inside a row
+    entity = tmp_path / "entity.xml"
+    entity.write_text(_vasprun_text(frames).replace("<v> 0.0 0.0 0.0 </v>\n   <v> 0.0 0.0 0.0 </v>\n  </varray>\n  <varray name=\"velocities\">",
+                                                    "<v> 0.0 0.0 0.0 </v>\n   <v> 0.25&#32;0.5 0.75 </v>\n  </varray>\n  <varray name=\"velocities\">", 1))
+    positions, _ = rio.read_vasprun_positions_ts(entity)
+    assert positions.shape == (2, 2, 3) and list(positions[0, 1]) == [0.25, 0.5, 0.75]

@@ -68,3 +68,28 @@ def test_corrections_bit_identical(ref):
     wn = np.linspace(1.0, 4000.0, 777)
     assert np.array_equal(get_bose_einstein_correction(wn, 300), ora.get_bose_einstein_correction(wn, 300))
     assert np.array_equal(get_laser_correction(wn, 1e7 / 532), ora.get_laser_correction(wn, 1e7 / 532))
+
+
+def test_vasprun_reader_matches_reference_live(ref, tmp_path):
+    """Next row N2: the native vasprun.xml reader against the unmodified reference reader
+    (``io/vasp/vasprun.py:298-330``, defusedxml stood in by the stdlib ElementTree) on a synthesised
+    file and on the reference's own malformed fixture."""
+    from ramannoodle.exceptions import InvalidFileException
+    from ramannoodle.io.vasp.vasprun import read_trajectory
+
+    from ramannoodle_b200 import io as rio
+    from test_ingest import _vasprun_text
+
+    rng = np.random.default_rng(11)
+    frames = rng.uniform(-2.0, 3.0, size=(23, 9, 3))
+    path = tmp_path / "vasprun.xml"
+    path.write_text(_vasprun_text(frames, potim="2.25"))
+    expected = read_trajectory(path)
+    positions, timestep = rio.read_vasprun_positions_ts(path, wrap=True)
+    assert timestep == expected.timestep == 2.25
+    assert np.array_equal(positions, expected.positions_ts)
+    malformed = os.path.join(os.path.dirname(ref.__file__), "..", "test", "data", "malformed", "vasprun.xml")
+    with pytest.raises(InvalidFileException, match="no trajectory found"):
+        read_trajectory(malformed)
+    with pytest.raises(rio.InvalidFileException, match="no trajectory found"):
+        rio.read_vasprun_positions_ts(malformed)

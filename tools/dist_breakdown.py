@@ -43,9 +43,9 @@ phases = {
     "eval_routed": lambda: model.calc_polarizabilities_routed(positions, ctx.ptr(rank, "series") + start * 72, peers,
                                                               start, ctx.period, ctx.width),
     "barrier_0": ctx.barrier,
-    "pack": lambda: lib.rn_spectrum_dist_pack(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "series")), ctx.table("work", group), stream),
+    "pack": lambda: lib.rn_spectrum_dist_pack(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "series")), ctx.table("work", group), -1, stream),
     "barrier_1": ctx.barrier,
-    "transform": lambda: lib.rn_spectrum_dist_transform(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "work")), ctx.table("recv", group), stream),
+    "transform": lambda: lib.rn_spectrum_dist_transform(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "work")), ctx.table("recv", group), -1, stream),
     "barrier_2": ctx.barrier,
     "final": lambda: lib.rn_spectrum_dist_final(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "recv")), ctx.table("power", world), world, stream),
     "barrier_3": ctx.barrier,

@@ -177,37 +177,42 @@ int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, double timeste
  *      and twiddle for this rank's n'; residue r is stored into peer_work[r] (rank r's work buffer);
  *   3. rn_spectrum_dist_transform: the local length-L/G convolution with this rank's decimated
  *      filter, in place in d_work; its last pass stores every value to the rank that owns that m'
- *      (peer_recv[owner]);
- *   4. rn_spectrum_dist_final: the G-point inverse DFT over the residues for this rank's m', and
- *      P[m] = sum_p |y_p[m]|^2 (plus this rank's share of the series energy) stored to every
- *      destination's power buffer;
- *   5. rn_spectrum_dist_combine (every rank): I[k] = (P[k] + P[M-k]) / (4 L^2) + E/2, wavenumbers and
- *      the optional corrections — exactly what rn_md_spectrum returns.
+ *      (peer_recv[owner]).  Ownership of m' is mirror-symmetric about (M mod L/G) / 2, so that the owner
+ *      of bin m also owns bin M - m;
+ *   4. rn_spectrum_dist_final: the G-point inverse DFT over the residues for this rank's pairs of m',
+ *      I[k] = (P[k] + P[M-k]) / (4 L^2) + E/2 with P[m] = sum_p |y_p[m]|^2 and the optional corrections,
+ *      stored to every destination's spectrum buffer (half the bytes of P, and nothing left to combine);
+ *      the wavenumbers are written locally (d_wavenumbers, may be NULL);
+ *   5. rn_spectrum_dist_finish (every rank): copies the finished intensities out of the spectrum buffer
+ *      (and writes the wavenumbers if d_wavenumbers is given: ranks that did not run step 4) — together
+ *      exactly what rn_md_spectrum returns.
  * The caller separates the steps with a cross-rank barrier (the buffers are peer-mapped device memory,
  * e.g. symmetric memory over NVLink) and provides, per rank, a work buffer, a receive buffer and a
- * power buffer of rn_spectrum_dist_sizes bytes.  All ranks of the world call every step; for spectator
- * ranks (rank >= G) steps 2-4 return immediately.  Steps 2 and 3 take `seq`: -1 handles the three packed
- * sequences in one go; 0, 1, 2 handle one sequence, so that a caller can pipeline them on several
- * streams (the NVLink-bound stores of one sequence overlap the transform of another; the pass with
- * seq = 0 also sums the series energies, and must be among the passes). */
+ * spectrum buffer of rn_spectrum_dist_sizes bytes (the spectrum buffer starts with 8 doubles: the series
+ * energy shares of the ranks, stored to every destination by step 2).  All ranks of the world call every
+ * step; for spectator ranks (rank >= G) steps 2-4 return immediately.  Steps 2 and 3 take `seq`: -1
+ * handles the three packed sequences in one go; 0, 1, 2 handle one sequence, so that a caller can
+ * pipeline them on several streams (the NVLink-bound stores of one sequence overlap the transform of
+ * another; the pass with seq = 0 also sums the series energies, and must be among the passes). */
 int rn_spectrum_plan_create_dist(int64_t num_frames, int device, int world, int rank,
                                  rn_spectrum_plan** out);
 /* info[0]=log2 L, [1]=ranks sharing the transform, [2]=log2 of the local length, [3]=strided levels,
  * [4],[5]=log2 of their radices, [6]=block of n' / m' one rank owns, [7]=M. */
 int rn_spectrum_plan_info(const rn_spectrum_plan* plan, int64_t info[8]);
 int rn_spectrum_dist_sizes(const rn_spectrum_plan* plan, int64_t* work_bytes, int64_t* recv_bytes,
-                           int64_t* power_bytes);
+                           int64_t* spectrum_bytes);
 int rn_spectrum_dist_route(const rn_spectrum_plan* plan, int64_t* period, int64_t* width);
 int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_series, double* const* peer_work,
-                          int seq, void* stream);
+                          double* const* dest_spectrum, int num_dest, int seq, void* stream);
 int rn_spectrum_dist_transform(rn_spectrum_plan* plan, double* d_work, double* const* peer_recv,
                                int seq, void* stream);
-int rn_spectrum_dist_final(rn_spectrum_plan* plan, const double* d_recv, double* const* dest_power,
-                           int num_dest, void* stream);
-int rn_spectrum_dist_combine(const rn_spectrum_plan* plan, const double* d_power, double timestep_fs,
-                             int laser_correction, double laser_wavelength_nm,
-                             int bose_einstein_correction, double temperature_K,
-                             double* d_wavenumbers, double* d_intensities, void* stream);
+int rn_spectrum_dist_final(rn_spectrum_plan* plan, const double* d_recv, const double* d_spectrum,
+                           double* const* dest_spectrum, int num_dest, double timestep_fs,
+                           int laser_correction, double laser_wavelength_nm,
+                           int bose_einstein_correction, double temperature_K,
+                           double* d_wavenumbers, void* stream);
+int rn_spectrum_dist_finish(const rn_spectrum_plan* plan, const double* d_spectrum, double timestep_fs,
+                            double* d_wavenumbers, double* d_intensities, void* stream);
 /* calc_signal_spectrum(signal, sampling_rate) (spectrum/utils.py:95-124) for one real signal of
  * length M = S-1 of the plan: outputs ceil(M/2) points (bin 0 included). */
 int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal, double sampling_rate,

@@ -159,15 +159,34 @@ __device__ __forceinline__ double2 tw_global(const Twiddles& T, uint32_t m) {
     return cmul(__ldg(T.hi + (m >> T.split)), __ldg(T.lo + (m & ((1u << T.split) - 1u))));
 }
 
-// Destination of the inverse transform's output when the transform is shared by G ranks: element
-// m' of this rank's residue sequence goes to the rank that owns m' (blocks of w = 2^log2w), into
-// slot (seq, source rank) of its receive buffer.
+// Destination of the inverse transform's output when the transform is shared by G ranks.  The spectrum
+// pairs bin m with bin M - m, whose residues m' = m mod Lh are mirror images, m'' = (c - m') mod Lh with
+// c = M mod Lh; ownership of m' is therefore MIRROR-SYMMETRIC, so that one rank holds both members of
+// every pair and finishes the pair's intensity by itself.  With u = (2 m' - c) mod 2 Lh and
+// a = min(u, 2 Lh - u) (the doubled circular distance from c/2, the same for m' and its mirror image),
+// the owner is min(a / w, G - 1), w = Lh / G; inside the owner's slice (seq, source rank) — w + 2 slots —
+// element a sits at (a - owner w) / 2 on the side u <= Lh and w/2 + 1 slots further on the other side.
 struct PeerOut {
     double2* ptr[8];
     int log2w;
+    int log2lh;
     int rank;
     int world;
+    int64_t c;  // M mod Lh
 };
+
+// owner of residue m1 and its slot within one (seq, source rank) slice of w + 2 slots
+__device__ __forceinline__ void mirror_owner(int64_t m1, int64_t c, int log2lh, int log2w, int world, int* owner,
+                                             int64_t* slot) {
+    const int64_t lh = (int64_t)1 << log2lh;
+    int64_t u = 2 * m1 - c;
+    if (u < 0) u += 2 * lh;
+    const bool far_side = u > lh;
+    const int64_t a = far_side ? 2 * lh - u : u;
+    const int o = min((int)(a >> log2w), world - 1);
+    *owner = o;
+    *slot = ((a - ((int64_t)o << log2w)) >> 1) + (far_side ? ((int64_t)1 << (log2w - 1)) + 1 : 0);
+}
 
 struct OutSpec {
     int mode;        // OUT_PLAIN / OUT_POWER / OUT_PEERS
@@ -182,9 +201,11 @@ __device__ __forceinline__ void store_out(const OutSpec& out, double2* plain, in
     } else if (out.mode == OUT_POWER) {
         if (m < out.M) out.power[(int64_t)seq * out.M + m] = v.x * v.x + v.y * v.y;
     } else {
-        const int owner = (int)(m >> out.peers.log2w);
-        const int64_t slot = (int64_t)(seq * out.peers.world + out.peers.rank) << out.peers.log2w;
-        out.peers.ptr[owner][slot + (m & (((int64_t)1 << out.peers.log2w) - 1))] = v;
+        int owner;
+        int64_t slot;
+        mirror_owner(m, out.peers.c, out.peers.log2lh, out.peers.log2w, out.peers.world, &owner, &slot);
+        const int64_t stride = ((int64_t)1 << out.peers.log2w) + 2;
+        out.peers.ptr[owner][(int64_t)(seq * out.peers.world + out.peers.rank) * stride + slot] = v;
     }
 }
 

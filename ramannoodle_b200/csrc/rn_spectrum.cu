@@ -95,6 +95,9 @@ struct PackParams {
     int seq_sel;           // -1: pack all three sequences; 0..2: only this one (0 also sums the energies)
     double* epart;         // [blocks] partials, then their sum
     unsigned int* ticket;  // zero between launches
+    double* share[8];      // shared transform: the sum also goes to slot `share_slot` of these spectrum buffers
+    int num_share;
+    int share_slot;
     Twiddles tw;
 };
 
@@ -114,7 +117,8 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 // Every pack block leaves its energy partial in epart[block]; the block that finishes last sums all
 // partials in index order (bit-reproducible whichever block that is) into epart[gridDim.x] and re-arms
 // the ticket counter.
-__device__ __forceinline__ void publish_energy(double block_total, double* epart, unsigned int* ticket, double* red) {
+__device__ __forceinline__ void publish_energy(double block_total, double* epart, unsigned int* ticket, double* red,
+                                               const PackParams* share = nullptr) {
     __shared__ bool last;
     if (threadIdx.x == 0) {
         epart[blockIdx.x] = block_total;
@@ -131,6 +135,8 @@ __device__ __forceinline__ void publish_energy(double block_total, double* epart
     if (threadIdx.x == 0) {
         epart[gridDim.x] = total;
         *ticket = 0;
+        if (share)  // this rank's share of the series energy, to every rank that forms intensities
+            for (int d = 0; d < share->num_share; d++) share->share[d][share->share_slot] = total;
     }
 }
 
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(kPackThreads) pack_alpha_kernel(const __grid_c
     }
     if (P.seq_sel <= 0) {  // uniform over the grid
         const double total = block_sum(energy, red);
-        publish_energy(total, P.epart, P.ticket, red);
+        publish_energy(total, P.epart, P.ticket, red, G > 1 ? &P : nullptr);
     }
 }
 
@@ -260,54 +266,6 @@ __global__ void __launch_bounds__(256) filter_fill_kernel(double2* __restrict__ 
     }
 }
 
-// ---- final stage of a shared transform: y[q Lh + m'] from the G residues, P = sum_p |y|^2 to every rank
-struct FinalParams {
-    const double2* recv;  // (3, G, w) slices z_r[m'] of this rank's block of m'
-    int64_t M, Lh;
-    int log2w;
-    int rank;
-    double* dest[8];      // (M + 8) doubles on every destination rank: P[m], then the energy partials by rank
-    int num_dest;
-    const double* epart;
-    int pack_blocks;
-    Twiddles tw;
-};
-
-template <int G>
-__global__ void __launch_bounds__(256) final_dist_kernel(const __grid_constant__ FinalParams P) {
-    constexpr int GH = G / 2;
-    const int64_t w = (int64_t)1 << P.log2w;
-    const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (local < w) {
-        const int64_t m1 = ((int64_t)P.rank << P.log2w) + local;  // m'
-        double2 w1 = fft::tw_global(P.tw, (uint32_t)m1);
-        w1.y = -w1.y;
-        double power[GH];
-#pragma unroll
-        for (int q = 0; q < GH; q++) power[q] = 0.0;
-#pragma unroll
-        for (int s = 0; s < 3; s++) {
-            double2 z[G];
-#pragma unroll
-            for (int r = 0; r < G; r++) z[r] = P.recv[((int64_t)(s * G + r) << P.log2w) + local];
-            fft::apply_powers<G>(z, w1);
-            fft::Dft<G, +1>::run(z);
-#pragma unroll
-            for (int q = 0; q < GH; q++) power[q] += z[q].x * z[q].x + z[q].y * z[q].y;
-        }
-#pragma unroll
-        for (int q = 0; q < GH; q++) {
-            const int64_t m = (int64_t)q * P.Lh + m1;
-            if (m < P.M)
-                for (int d = 0; d < P.num_dest; d++) P.dest[d][m] = power[q];
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // this rank's share of the series energy travels with the powers
-        const double total = P.epart[P.pack_blocks];
-        for (int d = 0; d < P.num_dest; d++) P.dest[d][P.M + P.rank] = total;
-    }
-}
-
 struct SpectrumParams {
     double timestep;
     int laser;
@@ -320,6 +278,115 @@ struct SpectrumParams {
 __device__ __forceinline__ double wavenumber_of(int64_t k, int64_t M, double dt) {
     const double val = 1.0 / ((double)M * dt);
     return ((double)k * val) * 33.35640951981521 * 1e3;
+}
+
+// laser / Bose-Einstein corrections of one point (_raman.py:13-69,303-307)
+__device__ __forceinline__ double corrected(double inten, double wn, const SpectrumParams& prm) {
+    if (prm.laser) {
+        const double r = (wn - prm.laser_wavenumber) / 10000.0;
+        const double r2 = r * r;
+        inten *= (r2 * r2) / wn;
+    }
+    if (prm.bose_einstein) {
+        const double en = wn * 29979245800.0 * 4.1357e-15;
+        inten *= 1.0 / (1.0 - exp(-en / prm.kt));
+    }
+    return inten;
+}
+
+// ---- final stage of a shared transform: y[q Lh + m'] from the G residues for a mirror pair of m', the
+// pair's finished intensities I[k] = (P[k] + P[M-k]) / (4 L^2) + E/2 (corrections included) to every rank
+constexpr int kSpecHeader = 8;  // spectrum buffer: energy shares of ranks 0..7, then the intensities
+
+struct FinalParams {
+    const double2* recv;  // (3, G, w + 2) slices z_r[m'] of the residues this rank owns (fft::mirror_owner)
+    int64_t M, Lh, c;     // c = M mod Lh
+    int log2w, log2lh;
+    int rank;
+    double* dest[8];      // spectrum buffers of the destination ranks
+    int num_dest;
+    const double* shares;  // this rank's spectrum buffer (energy shares written by the pack kernels)
+    int64_t points;
+    double scale;
+    SpectrumParams prm;
+    double* wn_out;       // local wavenumbers (points) or nullptr
+    Twiddles tw;
+};
+
+template <int G>
+__global__ void __launch_bounds__(256) final_dist_kernel(const __grid_constant__ FinalParams P) {
+    constexpr int GH = G / 2;
+    const int64_t w = (int64_t)1 << P.log2w;
+    const int64_t half = w >> 1;
+    const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pair number within this rank's slice
+    const int64_t a = ((int64_t)P.rank << P.log2w) + 2 * local + (P.c & 1);  // doubled distance from c/2
+    const bool valid = local < half || (local == half && P.rank == G - 1 && a == P.Lh);
+    if (valid) {
+        double energy = 0.0;
+#pragma unroll
+        for (int r = 0; r < G; r++) energy += P.shares[r];
+        const double econst = 0.5 * energy;
+        const bool self_paired = (a == 0 || a == P.Lh);
+        const int64_t stride = w + 2;
+        int64_t m1[2];
+        m1[0] = ((a + P.c) >> 1) & (P.Lh - 1);
+        m1[1] = ((2 * P.Lh + P.c - a) >> 1) & (P.Lh - 1);
+        double power[2][GH];
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+#pragma unroll
+            for (int q = 0; q < GH; q++) power[side][q] = 0.0;
+            if (side == 1 && self_paired) {
+#pragma unroll
+                for (int q = 0; q < GH; q++) power[1][q] = power[0][q];
+                continue;
+            }
+            double2 w1 = fft::tw_global(P.tw, (uint32_t)m1[side]);
+            w1.y = -w1.y;
+            const int64_t slot = local + (side ? half + 1 : 0);
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                double2 z[G];
+#pragma unroll
+                for (int r = 0; r < G; r++) z[r] = P.recv[(int64_t)(s * G + r) * stride + slot];
+                fft::apply_powers<G>(z, w1);
+                fft::Dft<G, +1>::run(z);
+#pragma unroll
+                for (int q = 0; q < GH; q++) power[side][q] += z[q].x * z[q].x + z[q].y * z[q].y;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < GH; q++) {
+            const int64_t m = (int64_t)q * P.Lh + m1[0];
+            if (m < 1 || m >= P.M) continue;
+            const int64_t m2 = P.M - m;  // its residue is m1[1]
+            const int q2 = (int)(m2 >> P.log2lh);
+            double partner = 0.0;
+#pragma unroll
+            for (int j = 0; j < GH; j++)
+                if (j == q2) partner = power[1][j];
+            const int64_t k = m < m2 ? m : m2;
+            if (k > P.points) continue;  // the middle bin of an even M is not part of the spectrum
+            const double first = m < m2 ? power[0][q] : partner, second = m < m2 ? partner : power[0][q];
+            double inten = (first + second) * P.scale + econst;  // (P[k] + P[M-k]) in that order
+            inten = corrected(inten, wavenumber_of(k, P.M, P.prm.timestep), P.prm);
+            for (int d = 0; d < P.num_dest; d++) P.dest[d][kSpecHeader + k - 1] = inten;
+        }
+    }
+    if (P.wn_out)  // the wavenumbers do not travel: every rank writes its own while the stores above drain
+        for (int64_t o = local; o < P.points; o += (int64_t)gridDim.x * blockDim.x)
+            P.wn_out[o] = wavenumber_of(o + 1, P.M, P.prm.timestep);
+}
+
+// after the last barrier: the finished intensities out of the spectrum buffer (and, for ranks that did not run
+// the final stage, the wavenumbers)
+__global__ void __launch_bounds__(256) finish_dist_kernel(const double* __restrict__ spec, int64_t points, int64_t M,
+                                                          double timestep, double* __restrict__ wn_out,
+                                                          double* __restrict__ int_out) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < points; o += (int64_t)gridDim.x * blockDim.x) {
+        int_out[o] = spec[kSpecHeader + o];
+        if (wn_out) wn_out[o] = wavenumber_of(o + 1, M, timestep);
+    }
 }
 
 // I[k] = (P[k] + P[M-k]) / (4 L^2) + E/2 for k = 1 .. ceil(M/2)-1 (bin 0 dropped, _raman.py:299-301),
@@ -341,19 +408,9 @@ __global__ void __launch_bounds__(256) combine_md_kernel(const double* __restric
         const int64_t k = o + 1;
         double sum = 0.0;
         for (int s = 0; s < nseq; s++) sum += power[(int64_t)s * M + k] + power[(int64_t)s * M + (M - k)];
-        double inten = sum * scale + econst;
         const double wn = wavenumber_of(k, M, prm.timestep);
-        if (prm.laser) {
-            const double r = (wn - prm.laser_wavenumber) / 10000.0;
-            const double r2 = r * r;
-            inten *= (r2 * r2) / wn;
-        }
-        if (prm.bose_einstein) {
-            const double en = wn * 29979245800.0 * 4.1357e-15;
-            inten *= 1.0 / (1.0 - exp(-en / prm.kt));
-        }
         wn_out[o] = wn;
-        int_out[o] = inten;
+        int_out[o] = corrected(sum * scale + econst, wn, prm);
     }
 }
 
@@ -685,6 +742,9 @@ extern "C" int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, dou
     pp.dst[0] = plan->d_work;
     pp.aligned16 = (reinterpret_cast<uintptr_t>(pp.src) % 16 == 0) ? 1 : 0;
     pp.seq_sel = -1;
+    pp.num_share = 0;
+    pp.share_slot = 0;
+    for (int i = 0; i < 8; i++) pp.share[i] = nullptr;
     pp.epart = plan->d_epart;
     pp.ticket = plan->d_ticket;
     pp.tw = plan_twiddles(plan);
@@ -726,6 +786,9 @@ extern "C" int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal
     pp.dst[0] = plan->d_work;
     pp.aligned16 = (reinterpret_cast<uintptr_t>(pp.src) % 16 == 0) ? 1 : 0;
     pp.seq_sel = -1;
+    pp.num_share = 0;
+    pp.share_slot = 0;
+    for (int i = 0; i < 8; i++) pp.share[i] = nullptr;
     pp.epart = plan->d_epart;
     pp.ticket = plan->d_ticket;
     pp.tw = plan_twiddles(plan);
@@ -749,11 +812,12 @@ extern "C" int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal
 // ---- one transform shared by the ranks of a process group -----------------------------------------
 
 extern "C" int rn_spectrum_dist_sizes(const rn_spectrum_plan* plan, int64_t* work_bytes, int64_t* recv_bytes,
-                                      int64_t* power_bytes) {
-    RN_CHECK_ARG(plan && work_bytes && recv_bytes && power_bytes, "null pointer");
+                                      int64_t* spectrum_bytes) {
+    RN_CHECK_ARG(plan && work_bytes && recv_bytes && spectrum_bytes, "null pointer");
     *work_bytes = (int64_t)sizeof(double2) * 3 * plan->Lh;
-    *recv_bytes = (int64_t)sizeof(double2) * 3 * plan->Lh;  // 3 sequences x G residues x (Lh / G) owned m'
-    *power_bytes = (int64_t)sizeof(double) * (plan->M + 8);
+    // 3 sequences x G residues x (Lh / G + 2) slots for the m' this rank owns (fft::mirror_owner)
+    *recv_bytes = (int64_t)sizeof(double2) * 3 * (plan->Lh + 2 * plan->world);
+    *spectrum_bytes = (int64_t)sizeof(double) * (kSpecHeader + rn_spectrum_num_points(plan->S));
     return RN_OK;
 }
 
@@ -773,9 +837,10 @@ static int launch_pack_dist(const rn_spectrum_plan* plan, const PackParams& pp, 
 }
 
 extern "C" int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_series, double* const* peer_work,
-                                     int seq, void* stream) {
-    RN_CHECK_ARG(plan && d_series && peer_work, "null pointer");
+                                     double* const* dest_spectrum, int num_dest, int seq, void* stream) {
+    RN_CHECK_ARG(plan && d_series && peer_work && dest_spectrum, "null pointer");
     RN_CHECK_ARG(seq >= -1 && seq <= 2, "seq must be -1 (all) or 0..2");
+    RN_CHECK_ARG(num_dest >= 1 && num_dest <= 8, "between 1 and 8 destinations");
     if (plan->rank >= plan->world) return RN_OK;  // spectator
     RN_CHECK_ARG(plan->world > 1, "rn_spectrum_dist_pack needs a plan from rn_spectrum_plan_create_dist with world > 1");
     DeviceGuard guard(plan->device);
@@ -793,10 +858,19 @@ extern "C" int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_ser
     }
     pp.aligned16 = (reinterpret_cast<uintptr_t>(pp.src) % 16 == 0) ? 1 : 0;
     pp.seq_sel = -1;
+    pp.num_share = 0;
+    pp.share_slot = 0;
+    for (int i = 0; i < 8; i++) pp.share[i] = nullptr;
     pp.epart = plan->d_epart;
     pp.ticket = plan->d_ticket;
     pp.tw = plan_twiddles(plan);
     pp.seq_sel = seq;
+    for (int d = 0; d < num_dest; d++) {
+        RN_CHECK_ARG(dest_spectrum[d] != nullptr, "null spectrum buffer pointer %d", d);
+        pp.share[d] = dest_spectrum[d];
+    }
+    pp.num_share = num_dest;
+    pp.share_slot = plan->rank;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (plan->world == 2) return launch_pack_dist<2>(plan, pp, s);
     if (plan->world == 4) return launch_pack_dist<4>(plan, pp, s);
@@ -817,6 +891,8 @@ extern "C" int rn_spectrum_dist_transform(rn_spectrum_plan* plan, double* d_work
     int log2w = plan->log2lh;
     for (int g = plan->world; g > 1; g >>= 1) log2w--;
     out.peers.log2w = log2w;
+    out.peers.log2lh = plan->log2lh;
+    out.peers.c = plan->M & (plan->Lh - 1);
     for (int r = 0; r < plan->world; r++) {
         RN_CHECK_ARG(peer_recv[r] != nullptr, "null receive buffer pointer for rank %d", r);
         out.peers.ptr[r] = reinterpret_cast<double2*>(peer_recv[r]);
@@ -829,37 +905,49 @@ extern "C" int rn_spectrum_dist_transform(rn_spectrum_plan* plan, double* d_work
 
 template <int G>
 static int launch_final_dist(const rn_spectrum_plan* plan, const FinalParams& fp, cudaStream_t s) {
-    const int64_t w = (int64_t)1 << fp.log2w;
-    final_dist_kernel<G><<<(unsigned)((w + 255) / 256), 256, 0, s>>>(fp);
+    const int64_t pairs = ((int64_t)1 << (fp.log2w - 1)) + 1;
+    final_dist_kernel<G><<<(unsigned)((pairs + 255) / 256), 256, 0, s>>>(fp);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     (void)plan;
     return RN_OK;
 }
 
-extern "C" int rn_spectrum_dist_final(rn_spectrum_plan* plan, const double* d_recv, double* const* dest_power,
-                                      int num_dest, void* stream) {
-    RN_CHECK_ARG(plan && dest_power, "null pointer");
+extern "C" int rn_spectrum_dist_final(rn_spectrum_plan* plan, const double* d_recv, const double* d_spectrum,
+                                      double* const* dest_spectrum, int num_dest, double timestep_fs,
+                                      int laser_correction, double laser_wavelength_nm, int bose_einstein_correction,
+                                      double temperature_K, double* d_wavenumbers, void* stream) {
+    RN_CHECK_ARG(plan && dest_spectrum, "null pointer");
+    RN_CHECK_ARG(timestep_fs > 0, "timestep must be positive");
+    if (laser_correction) RN_CHECK_ARG(laser_wavelength_nm > 0, "invalid laser_wavelength");
+    if (bose_einstein_correction) RN_CHECK_ARG(temperature_K > 0, "invalid temperature: %g <= 0", temperature_K);
     if (plan->rank >= plan->world) return RN_OK;
-    RN_CHECK_ARG(plan->world > 1 && d_recv, "rn_spectrum_dist_final needs a shared plan and its receive buffer");
+    RN_CHECK_ARG(plan->world > 1 && d_recv && d_spectrum,
+                 "rn_spectrum_dist_final needs a shared plan, its receive buffer and its spectrum buffer");
     RN_CHECK_ARG(num_dest >= 1 && num_dest <= 8, "between 1 and 8 destinations");
     DeviceGuard guard(plan->device);
     FinalParams fp;
     fp.recv = reinterpret_cast<const double2*>(d_recv);
     fp.M = plan->M;
     fp.Lh = plan->Lh;
+    fp.c = plan->M & (plan->Lh - 1);
     int log2w = plan->log2lh;
     for (int g = plan->world; g > 1; g >>= 1) log2w--;
     fp.log2w = log2w;
+    fp.log2lh = plan->log2lh;
     fp.rank = plan->rank;
     for (int i = 0; i < 8; i++) fp.dest[i] = nullptr;
     for (int d = 0; d < num_dest; d++) {
-        RN_CHECK_ARG(dest_power[d] != nullptr, "null destination pointer %d", d);
-        fp.dest[d] = dest_power[d];
+        RN_CHECK_ARG(dest_spectrum[d] != nullptr, "null destination pointer %d", d);
+        fp.dest[d] = dest_spectrum[d];
     }
     fp.num_dest = num_dest;
-    fp.epart = plan->d_epart;
-    fp.pack_blocks = plan->pack_blocks;
+    fp.shares = d_spectrum;
+    fp.points = rn_spectrum_num_points(plan->S);
+    fp.scale = 0.25 / ((double)plan->L * (double)plan->L);
+    fp.prm = spectrum_params(timestep_fs, laser_correction, laser_wavelength_nm, bose_einstein_correction,
+                             temperature_K);
+    fp.wn_out = d_wavenumbers;
     fp.tw = plan_twiddles(plan);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (plan->world == 2) return launch_final_dist<2>(plan, fp, s);
@@ -867,23 +955,18 @@ extern "C" int rn_spectrum_dist_final(rn_spectrum_plan* plan, const double* d_re
     return launch_final_dist<8>(plan, fp, s);
 }
 
-extern "C" int rn_spectrum_dist_combine(const rn_spectrum_plan* plan, const double* d_power, double timestep_fs,
-                                        int laser_correction, double laser_wavelength_nm, int bose_einstein_correction,
-                                        double temperature_K, double* d_wavenumbers, double* d_intensities,
-                                        void* stream) {
-    RN_CHECK_ARG(plan != nullptr && d_power != nullptr, "null pointer");
+extern "C" int rn_spectrum_dist_finish(const rn_spectrum_plan* plan, const double* d_spectrum, double timestep_fs,
+                                       double* d_wavenumbers, double* d_intensities, void* stream) {
+    RN_CHECK_ARG(plan != nullptr && d_spectrum != nullptr, "null pointer");
     RN_CHECK_ARG(timestep_fs > 0, "timestep must be positive");
-    if (laser_correction) RN_CHECK_ARG(laser_wavelength_nm > 0, "invalid laser_wavelength");
-    if (bose_einstein_correction) RN_CHECK_ARG(temperature_K > 0, "invalid temperature: %g <= 0", temperature_K);
     const int64_t points = rn_spectrum_num_points(plan->S);
     if (points == 0) return RN_OK;
-    RN_CHECK_ARG(d_wavenumbers && d_intensities, "null output pointer");
+    RN_CHECK_ARG(d_intensities, "null output pointer");
     DeviceGuard guard(plan->device);
-    const SpectrumParams prm = spectrum_params(timestep_fs, laser_correction, laser_wavelength_nm,
-                                               bose_einstein_correction, temperature_K);
-    const double scale = 0.25 / ((double)plan->L * (double)plan->L);
-    combine_md_kernel<<<grid_for(points, plan->sm_count ? plan->sm_count : 148), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        d_power, 1, d_power + plan->M, plan->world, plan->M, scale, points, prm, d_wavenumbers, d_intensities);
+    int sms = plan->sm_count;
+    if (sms <= 0) sms = 148;
+    finish_dist_kernel<<<grid_for(points, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_spectrum, points, plan->M, timestep_fs, d_wavenumbers, d_intensities);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     return RN_OK;

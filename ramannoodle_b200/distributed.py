@@ -135,8 +135,8 @@ class _SharedContext:
 
         series_bytes = align(self.num_frames * 72)
         self.offsets = {"series": 0, "work": series_bytes, "recv": series_bytes + align(sizes[0].value),
-                        "power": series_bytes + align(sizes[0].value) + align(sizes[1].value)}
-        total = self.offsets["power"] + align(sizes[2].value)
+                        "spectrum": series_bytes + align(sizes[0].value) + align(sizes[1].value)}
+        total = self.offsets["spectrum"] + align(sizes[2].value)
         pg = group if group is not None else dist.group.WORLD
         ok = True
         self.buffer = self.handle = None
@@ -329,7 +329,8 @@ class ShardedMDRamanSpectrum(MDRamanSpectrum):
                         lane.wait_event(packed)
                     with torch.cuda.stream(lane):
                         lane_stream = ctypes.c_void_p(lane.cuda_stream)
-                        _lib.check(lib.rn_spectrum_dist_pack(ctx.plan, series_ptr, ctx.table("work", group), seq,
+                        _lib.check(lib.rn_spectrum_dist_pack(ctx.plan, series_ptr, ctx.table("work", group),
+                                                             ctx.table("spectrum", ctx.world), ctx.world, seq,
                                                              lane_stream), "rn_spectrum_dist_pack")
                         packed = torch.cuda.Event()
                         packed.record(lane)
@@ -343,22 +344,27 @@ class ShardedMDRamanSpectrum(MDRamanSpectrum):
                 for done in finished:
                     current.wait_event(done)
             else:
-                _lib.check(lib.rn_spectrum_dist_pack(ctx.plan, series_ptr, ctx.table("work", group), -1, stream),
+                _lib.check(lib.rn_spectrum_dist_pack(ctx.plan, series_ptr, ctx.table("work", group),
+                                                     ctx.table("spectrum", ctx.world), ctx.world, -1, stream),
                            "rn_spectrum_dist_pack")
                 ctx.barrier()  # every residue of every block has landed in the work buffers
                 _lib.check(lib.rn_spectrum_dist_transform(ctx.plan, work_ptr, ctx.table("recv", group), -1, stream),
                            "rn_spectrum_dist_transform")
-            ctx.barrier()  # every rank holds all residues of its output block
-            _lib.check(lib.rn_spectrum_dist_final(ctx.plan, ctypes.c_void_p(ctx.ptr(ctx.rank, "recv")),
-                                                  ctx.table("power", ctx.world), ctx.world, stream),
-                       "rn_spectrum_dist_final")
-            ctx.barrier()  # P and the energy shares are complete on every rank
-            status = lib.rn_spectrum_dist_combine(
-                ctx.plan, ctypes.c_void_p(ctx.ptr(ctx.rank, "power")), float(self._timestep),
-                1 if laser_correction else 0, float(laser_wavelength) if laser_correction else 0.0,
-                1 if bose_einstein_correction else 0, float(temperature) if bose_einstein_correction else 0.0,
-                ctypes.c_void_p(wavenumbers.data_ptr()), ctypes.c_void_p(intensities.data_ptr()), stream)
-            _lib.check(status, "rn_spectrum_dist_combine")
+            ctx.barrier()  # every rank holds all residues of the bin pairs it owns (and every energy share)
+            spectrum_ptr = ctypes.c_void_p(ctx.ptr(ctx.rank, "spectrum"))
+            transforms = ctx.rank < group
+            status = lib.rn_spectrum_dist_final(
+                ctx.plan, ctypes.c_void_p(ctx.ptr(ctx.rank, "recv")), spectrum_ptr, ctx.table("spectrum", ctx.world),
+                ctx.world, float(self._timestep), 1 if laser_correction else 0,
+                float(laser_wavelength) if laser_correction else 0.0, 1 if bose_einstein_correction else 0,
+                float(temperature) if bose_einstein_correction else 0.0,
+                ctypes.c_void_p(wavenumbers.data_ptr()) if transforms else None, stream)
+            _lib.check(status, "rn_spectrum_dist_final")
+            ctx.barrier()  # the finished intensities of every owner have landed on every rank
+            _lib.check(lib.rn_spectrum_dist_finish(ctx.plan, spectrum_ptr, float(self._timestep),
+                                                   None if transforms else ctypes.c_void_p(wavenumbers.data_ptr()),
+                                                   ctypes.c_void_p(intensities.data_ptr()), stream),
+                       "rn_spectrum_dist_finish")
         return wavenumbers, intensities
 
 

@@ -266,3 +266,44 @@ def md_intensities(alpha, world: int = 1):
     points = (m_len + 1) // 2 - 1
     k = np.arange(1, points + 1)
     return (power[k] + power[m_len - k]) * (0.25 / (float(big) * float(big))) + 0.5 * energy
+
+
+def mirror_owner(m1: int, c: int, log2lh: int, log2w: int, world: int):
+    """csrc/rn_fft.cuh: mirror_owner — (owner rank, slot in the owner's slice of w + 2 slots) of residue m1."""
+    lh = 1 << log2lh
+    u = 2 * m1 - c
+    if u < 0:
+        u += 2 * lh
+    far_side = u > lh
+    a = 2 * lh - u if far_side else u
+    owner = min(a >> log2w, world - 1)
+    return owner, ((a - (owner << log2w)) >> 1) + (((1 << (log2w - 1)) + 1) if far_side else 0)
+
+
+def final_pairs(rank: int, num_bins: int, log2lh: int, world: int):
+    """csrc/rn_spectrum.cu: final_dist_kernel — for every pair slot of `rank`: the two residues it reads and
+    the bins k it finishes (each with the (q, side) of P[k] and of P[M-k])."""
+    lh = 1 << log2lh
+    log2w = log2lh - (world.bit_length() - 1)
+    w, half = 1 << log2w, 1 << (log2w - 1)
+    c = num_bins & (lh - 1)
+    points = (num_bins + 1) // 2 - 1
+    out = []
+    for local in range(half + 1):
+        a = (rank << log2w) + 2 * local + (c & 1)
+        if not (local < half or (local == half and rank == world - 1 and a == lh)):
+            continue
+        m_near = ((a + c) >> 1) & (lh - 1)
+        m_far = ((2 * lh + c - a) >> 1) & (lh - 1)
+        bins = []
+        for q in range(world // 2):
+            m = q * lh + m_near
+            if m < 1 or m >= num_bins:
+                continue
+            m2 = num_bins - m
+            k = min(m, m2)
+            if k > points:
+                continue
+            bins.append((k, m, m2, m2 >> log2lh))
+        out.append((local, local + half + 1, m_near, m_far, bins))
+    return out

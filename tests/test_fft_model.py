@@ -64,3 +64,39 @@ def test_measure_model_matches_oracle(frames, world):
     _, ref = ora.md_measure(alpha, 1.0)
     got = fm.md_intensities(alpha, world)
     assert np.abs(got / ref - 1).max() < 1e-11
+
+
+@pytest.mark.parametrize("num_bins, log2lh, world", [(40, 6, 2), (41, 6, 2), (100, 6, 4), (127, 6, 4), (128, 6, 4),
+                                                     (255, 6, 8), (256, 6, 8), (250, 6, 8), (8999, 12, 8), (8000, 12, 4)])
+def test_mirror_ownership_of_shared_transform(num_bins, log2lh, world):
+    """Index logic of the shared transform's last two steps (store_out's mirror_owner and the pair
+    enumeration of final_dist_kernel), restated in tests/fft_model.py: every residue has exactly one
+    (owner, slot); a residue and its mirror image share the owner; the owners' pair lists finish every
+    bin k = 1..points exactly once (self-paired residues: twice, with the same operands)."""
+    lh = 1 << log2lh
+    assert num_bins <= (world // 2) * lh
+    log2w = log2lh - (world.bit_length() - 1)
+    w = 1 << log2w
+    c = num_bins & (lh - 1)
+    seen = {}
+    for m1 in range(lh):
+        owner, slot = fm.mirror_owner(m1, c, log2lh, log2w, world)
+        assert 0 <= owner < world and 0 <= slot < w + 2
+        assert (owner, slot) not in seen
+        seen[(owner, slot)] = m1
+        mirror = (c - m1) % lh
+        assert fm.mirror_owner(mirror, c, log2lh, log2w, world)[0] == owner
+    points = (num_bins + 1) // 2 - 1
+    finished = {}
+    for rank in range(world):
+        for near_slot, far_slot, m_near, m_far, bins in fm.final_pairs(rank, num_bins, log2lh, world):
+            assert seen[(rank, near_slot)] == m_near
+            if m_far != m_near:
+                assert seen[(rank, far_slot)] == m_far
+            for k, m, m2, q2 in bins:
+                assert m % lh == m_near and m2 % lh == m_far and m2 // lh == q2 < world // 2
+                assert {m, m2} == {k, num_bins - k}
+                if k in finished:
+                    assert m_near == m_far  # a self-paired residue meets its pair from both ends
+                finished[k] = finished.get(k, 0) + 1
+    assert sorted(finished) == list(range(1, points + 1))

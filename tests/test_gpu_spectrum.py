@@ -233,7 +233,7 @@ def _emulated_shared_measure(alpha, timestep, world, by_sequence=False, **correc
         assert lib.rn_spectrum_dist_sizes(plans[0], *[ctypes.byref(v) for v in sizes]) == 0
         work = [torch.full((sizes[0].value // 8,), float("nan"), dtype=torch.float64, device="cuda:0") for _ in range(world)]
         recv = [torch.full((sizes[1].value // 8,), float("nan"), dtype=torch.float64, device="cuda:0") for _ in range(world)]
-        power = [torch.full((sizes[2].value // 8,), float("nan"), dtype=torch.float64, device="cuda:0") for _ in range(world)]
+        spec = [torch.full((sizes[2].value // 8,), float("nan"), dtype=torch.float64, device="cuda:0") for _ in range(world)]
         info = (ctypes.c_int64 * 8)()
         assert lib.rn_spectrum_plan_info(plans[0], info) == 0
         group = int(info[1])
@@ -245,23 +245,27 @@ def _emulated_shared_measure(alpha, timestep, world, by_sequence=False, **correc
         for seq in ((-1,) if not by_sequence else (2, 0, 1)):
             for rank in range(world):
                 assert lib.rn_spectrum_dist_pack(plans[rank], ctypes.c_void_p(d_alpha.data_ptr()), table(work[:group]),
-                                                 seq, stream) == 0
+                                                 table(spec), world, seq, stream) == 0
             for rank in range(world):
                 assert lib.rn_spectrum_dist_transform(plans[rank], ctypes.c_void_p(work[rank].data_ptr()),
                                                       table(recv[:group]), seq, stream) == 0
-        for rank in range(world):
-            assert lib.rn_spectrum_dist_final(plans[rank], ctypes.c_void_p(recv[rank].data_ptr()), table(power), world,
-                                              stream) == 0
         points = int(lib.rn_spectrum_num_points(frames))
+        laser = (1 if "laser_wavelength" in corrections else 0, float(corrections.get("laser_wavelength", 0.0)))
+        bose = (1 if "temperature" in corrections else 0, float(corrections.get("temperature", 0.0)))
+        outputs = [(torch.full((points,), float("nan"), dtype=torch.float64, device="cuda:0"),
+                    torch.full((points,), float("nan"), dtype=torch.float64, device="cuda:0")) for _ in range(world)]
+        for rank in range(world):
+            assert lib.rn_spectrum_dist_final(plans[rank], ctypes.c_void_p(recv[rank].data_ptr()),
+                                              ctypes.c_void_p(spec[rank].data_ptr()), table(spec), world, float(timestep),
+                                              *laser, *bose,
+                                              ctypes.c_void_p(outputs[rank][0].data_ptr()) if rank < group else None,
+                                              stream) == 0
         results = []
         for rank in range(world):
-            wn = torch.empty(points, dtype=torch.float64, device="cuda:0")
-            inten = torch.empty(points, dtype=torch.float64, device="cuda:0")
-            assert lib.rn_spectrum_dist_combine(
-                plans[rank], ctypes.c_void_p(power[rank].data_ptr()), float(timestep),
-                1 if "laser_wavelength" in corrections else 0, float(corrections.get("laser_wavelength", 0.0)),
-                1 if "temperature" in corrections else 0, float(corrections.get("temperature", 0.0)),
-                ctypes.c_void_p(wn.data_ptr()), ctypes.c_void_p(inten.data_ptr()), stream) == 0
+            wn, inten = outputs[rank]
+            assert lib.rn_spectrum_dist_finish(plans[rank], ctypes.c_void_p(spec[rank].data_ptr()), float(timestep),
+                                               None if rank < group else ctypes.c_void_p(wn.data_ptr()),
+                                               ctypes.c_void_p(inten.data_ptr()), stream) == 0
             results.append((wn.cpu().numpy(), inten.cpu().numpy()))
         return results
     finally:

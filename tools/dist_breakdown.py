@@ -43,14 +43,18 @@ phases = {
     "eval_routed": lambda: model.calc_polarizabilities_routed(positions, ctx.ptr(rank, "series") + start * 72, peers,
                                                               start, ctx.period, ctx.width),
     "barrier_0": ctx.barrier,
-    "pack": lambda: lib.rn_spectrum_dist_pack(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "series")), ctx.table("work", group), -1, stream),
+    "pack": lambda: lib.rn_spectrum_dist_pack(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "series")), ctx.table("work", group),
+                                                 ctx.table("spectrum", world), world, -1, stream),
     "barrier_1": ctx.barrier,
     "transform": lambda: lib.rn_spectrum_dist_transform(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "work")), ctx.table("recv", group), -1, stream),
     "barrier_2": ctx.barrier,
-    "final": lambda: lib.rn_spectrum_dist_final(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "recv")), ctx.table("power", world), world, stream),
+    "final": lambda: lib.rn_spectrum_dist_final(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "recv")), ctypes.c_void_p(ctx.ptr(rank, "spectrum")),
+                                                ctx.table("spectrum", world), world, 1.0, 0, 0.0, 0, 0.0,
+                                                ctypes.c_void_p(wn.data_ptr()) if rank < group else None, stream),
     "barrier_3": ctx.barrier,
-    "combine": lambda: lib.rn_spectrum_dist_combine(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "power")), 1.0, 0, 0.0, 0, 0.0,
-                                                    ctypes.c_void_p(wn.data_ptr()), ctypes.c_void_p(inten.data_ptr()), stream),
+    "finish": lambda: lib.rn_spectrum_dist_finish(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "spectrum")), 1.0,
+                                                  None if rank < group else ctypes.c_void_p(wn.data_ptr()),
+                                                  ctypes.c_void_p(inten.data_ptr()), stream),
 }
 names = list(phases)
 reps = 20

@@ -20,7 +20,7 @@ void rn_debug_force_generic_affine(int on);
 /* frames-per-tile multiplier (1, 2; 0 = automatic) of the TMA affine kernel */
 void rn_debug_set_affine_config(int mt, int stages);
 /* dense kernel generation: 1 = first, 3 = warp-specialised + Horner epilogue, 4 = chained-DMMA epilogue */
-void rn_debug_set_dense_config(int version, int unused);
+void rn_debug_set_dense_config(int version, int variant);  /* variant (generation 4): bit 0 = one-DADD wrap with a branch in the producers, bit 1 = DOF padding computed, bits 4-7 = ring slots (4..7, 0 = automatic) */
 /* unit-balanced dense schedule: 0 = never, 1 = automatic, 2 = always */
 void rn_debug_set_dense_split(int mode);
 /* mask sweeps: fused sweep kernels on/off; shortest run of linear models worth fusing (2..4) */

@@ -28,6 +28,8 @@ namespace rn {
 // the piecewise-polynomial epilogue, 4 = warp-specialised with the chained-DMMA epilogue (default)
 // A/B switches (include/ramannoodle_b200_debug.h): atomics, read once per launch
 static std::atomic<int> g_dense_version{4};
+static std::atomic<int> g_dense_variant{0};  // A/B bits: 1 = one-DADD wrap with a branch in the producers, 2 = compute the DOF padding
+static std::atomic<int> g_dense_stages{kTpStagesDefault};
 static std::atomic<int> g_dense_split{1};  // 0 = never, 1 = when whole tiles would leave SMs idle, 2 = always (tests)
 
 // ------------------------------------------------------------------------------------
@@ -256,7 +258,8 @@ static int launch_tp_cfg(const rn_model* m, const double* d_in, bool wrap, bool 
     const int K = (int)m->dim;
     constexpr int FT = 128;
     const bool align16 = (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (K % 2 == 0);
-    const size_t smem = ((size_t)kStages2 * (FT + kJT2) * kRS2) * sizeof(double) + 128;
+    const int stages = tp_stages(g_dense_stages.load(std::memory_order_relaxed), align16);
+    const size_t smem = tp_smem_bytes(stages);
     const int64_t tiles = (num_frames + FT - 1) / FT;
     int grid = (int)std::min<int64_t>(tiles, m->sm_count);
     // Whole frame tiles per CTA leave SMs idle in the last wave when there are few tiles per SM
@@ -291,7 +294,7 @@ static int launch_tp_cfg(const rn_model* m, const double* d_in, bool wrap, bool 
         RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
         kern<<<grid, 384, smem, stream>>>(d_in, m->d_ref_wrapped, V, m->d_tp_x0, m->d_tp_brk, num_frames, K, \
                                           (int)m->v_cols, (int)m->dense_pad, (int)m->num_dense, accumulate ? 1 : 0,             \
-                                          split ? 1 : 0, mk, peers);                                         \
+                                          (split ? 1 : 0) | (g_dense_variant.load(std::memory_order_relaxed) << 1), stages, mk, peers);                                         \
     }
     if (wrap) {
         if (align16) RN_TP_LAUNCH(true, true) else RN_TP_LAUNCH(true, false)
@@ -396,8 +399,11 @@ int launch_dense(const rn_model* m, const double* d_in, bool wrap, bool accumula
 }  // namespace rn
 
 // Test / tuning hooks (not in the public header).
-extern "C" void rn_debug_set_dense_config(int version, int unused) {
-    (void)unused;
+extern "C" void rn_debug_set_dense_config(int version, int variant) {
+    // variant: bits 0-1 = A/B switches, bits 4-7 = ring slots of the chained-epilogue kernel (0 = default)
+    const int stages = (variant >> 4) & 15;
+    rn::g_dense_stages.store(stages, std::memory_order_relaxed);
+    rn::g_dense_variant.store(variant & 3, std::memory_order_relaxed);
     rn::g_dense_version.store(version, std::memory_order_relaxed);
 }
 // 0 = whole frame tiles per CTA, 1 = automatic (default), 2 = always balance (frame tile, DOF tile) units

@@ -19,7 +19,8 @@ static int launch_tp_sweep_cfg(const rn_model* const* models, const double* d_in
     const int K = (int)m->dim;
     constexpr int FT = 128;
     const bool align16 = (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (K % 2 == 0);
-    const size_t smem = ((size_t)kStages2 * (FT + kJT2) * kRS2) * sizeof(double) + 128;
+    const int stages = tp_stages(0, align16);
+    const size_t smem = tp_smem_bytes(stages);
     const int64_t tiles = (num_frames + FT - 1) / FT;
     int grid = (int)std::min<int64_t>(tiles, m->sm_count);
     // unit-balanced schedule for short trajectories, as in rn_dense.cu: launch_tp_cfg
@@ -53,7 +54,7 @@ static int launch_tp_sweep_cfg(const rn_model* const* models, const double* d_in
         RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
         kern<<<grid, 384, smem, stream>>>(d_in, m->d_ref_wrapped, m->d_v_frac, m->d_tp_x0, m->d_tp_brk,         \
                                           num_frames, K, (int)m->v_cols, (int)m->dense_pad, (int)m->num_dense, accumulate ? 1 : 0, \
-                                          split ? 1 : 0, mk, peers);                                            \
+                                          split ? 1 : 0, stages, mk, peers);                                            \
     }
     if (align16) RN_TP_SWEEP_LAUNCH(true) else RN_TP_SWEEP_LAUNCH(false)
 #undef RN_TP_SWEEP_LAUNCH

@@ -3,6 +3,8 @@
 // sweeps: NG masked copies of one model share the projection, the epilogue runs once per mask).
 #pragma once
 
+#include <type_traits>
+
 #include "rn_device.cuh"
 
 namespace rn {
@@ -12,6 +14,19 @@ constexpr int kKC2 = 16;      // K elements per pipeline chunk
 constexpr int kRS2 = 20;      // padded smem row stride (doubles): conflict-free fragment loads
 constexpr int kStages2 = 4;
 constexpr int kAmpStride = 65;  // doubles per frame row of the amplitude tile
+constexpr int kTpStagesDefault = 0;  // automatic: tp_stages()
+
+// Ring depth (measured on the bench shapes, tools/run_dense_cases.py): 7 slots (215 KB) for 16-byte copies;
+// 6 when odd row lengths force the 8-byte cp.async.ca path, which wants some L1 left beside the ring.
+inline int tp_stages(int requested, bool align16) {
+    if (requested >= 4 && requested <= 7) return requested;
+    return align16 ? 7 : 6;
+}
+
+// shared memory of dense_kernel_tp with `stages` ring slots (128-frame tiles)
+inline size_t tp_smem_bytes(int stages) {
+    return ((size_t)stages * (128 + kJT2) * kRS2) * sizeof(double) + 128;
+}
 
 
 __device__ __forceinline__ void mbar_init2(uint32_t bar, uint32_t count) {
@@ -53,7 +68,7 @@ template <int DEG, int NBK, bool FULL, bool WRAP, bool ALIGN16, int NG>
 __global__ void __launch_bounds__(384, 1)
     dense_kernel_tp(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ V,
                     const double* __restrict__ tp_x0, const double* __restrict__ tp_brk, int64_t num_frames, int K,
-                    int Kv, int Jpad, int Jreal, int accumulate, int split, TpMasks<NG> mk, AlphaPeers peers) {
+                    int Kv, int Jpad, int Jreal, int accumulate, int split, int stages, TpMasks<NG> mk, AlphaPeers peers) {
     constexpr int FT = 128;    // frames per tile: 8 MMA warps x 16
     constexpr int MMAW = 8;    // MMA warps (two per scheduler: one covers the other's LDS / barrier bubbles)
     constexpr int MTW = 2;     // 8-frame groups per MMA warp
@@ -61,15 +76,20 @@ __global__ void __launch_bounds__(384, 1)
     constexpr int NF = DEG + NBK * PERB;      // features per DOF
     constexpr int NBS = NBK > 0 ? NBK : 1;    // stride of the break table
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* As = reinterpret_cast<double*>(smem_raw);          // [kStages2][FT][kRS2]
-    double* Bs = As + (size_t)kStages2 * FT * kRS2;            // [kStages2][kJT2][kRS2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + (size_t)kStages2 * kJT2 * kRS2);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages2);
+    // `stages` ring slots (4 .. 7, tp_stages()): the copies run two chunks ahead; every further slot lets the
+    // producers finish a chunk's displacements that much earlier than the MMA warps need it
+    double* As = reinterpret_cast<double*>(smem_raw);          // [stages][FT][kRS2]
+    double* Bs = As + (size_t)stages * FT * kRS2;              // [stages][kJT2][kRS2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + (size_t)stages * kJT2 * kRS2);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + stages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunks = Kv / kKC2;
     const int jtiles = Jpad / kJT2;
     const int64_t num_tiles = (num_frames + FT - 1) / FT;
+    // `split`: bit 0 = unit-balanced schedule; bits 1-2 = A/B variants (rn_debug_set_dense_config)
+    const bool fast_wrap = (split & 2) != 0, keep_padding = (split & 4) != 0;
+    split &= 1;
     // Work units are (frame tile, DOF tile) pairs; CTA b owns the contiguous range [u0, u1).  Normally
     // the ranges are whole frame tiles.  With `split` (few frame tiles per SM: short trajectories)
     // they are balanced to the unit, a frame tile shared by two CTAs is finished with atomic adds
@@ -86,7 +106,7 @@ __global__ void __launch_bounds__(384, 1)
     const int64_t tile_begin = u0 / jtiles, tile_end = (u1 + jtiles - 1) / jtiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages2; s++) {
+        for (int s = 0; s < stages; s++) {
             mbar_init2(full0 + 8 * s, 128);  // every producer thread arrives after its wrap items
             mbar_init2(empty0 + 8 * s, MMAW);  // one arrival per MMA warp
         }
@@ -109,8 +129,8 @@ __global__ void __launch_bounds__(384, 1)
         const double* v_src0 = V + (int64_t)b_row0 * Kv + b_seg * 2;
         const int w_row0 = ptid >> 3, w_seg = ptid & 7;
 
-        uint32_t issued = 0;   // chunks issued so far (running over all tiles: ring stage / parity)
-        uint32_t wrapped = 0;  // chunks handed to the MMA warps so far
+        // ring positions (running over all tiles): slot and round parity of the next chunk to issue / to wrap
+        uint32_t is_st = 0, is_round = 0, wr_st = 0;
         for (int64_t tile = tile_begin; tile < tile_end; tile++) {
             const int64_t frame0 = tile * FT;
             const int jt_lo = (int)(max(u0, tile * jtiles) - tile * jtiles);
@@ -125,8 +145,10 @@ __global__ void __launch_bounds__(384, 1)
             int is_kc = 0, is_jt = jt_lo;
             auto issue = [&]() {
                 if (is_jt < jt_hi) {
-                    const uint32_t st = issued & (kStages2 - 1);
-                    if (issued >= (uint32_t)kStages2) mbar_wait2(empty0 + 8 * st, ((issued >> 2) - 1) & 1);
+                    const uint32_t st = is_st;
+                    if (is_round > 0) {  // the slot's previous occupant (one round earlier) must have been consumed
+                        mbar_wait2(empty0 + 8 * st, (is_round - 1) & 1);
+                    }
                     const int col = is_kc * kKC2 + a_seg * A_ELEMS;
                     const int rem = K - col;
                     const int bytes = ALIGN16 ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : (rem >= 1 ? 8 : 0);
@@ -148,7 +170,10 @@ __global__ void __launch_bounds__(384, 1)
                         is_kc = 0;
                         ++is_jt;
                     }
-                    ++issued;
+                    if (++is_st == (uint32_t)stages) {
+                        is_st = 0;
+                        ++is_round;
+                    }
                 }
                 cp_async_commit();
             };
@@ -167,21 +192,21 @@ __global__ void __launch_bounds__(384, 1)
                 issue();             // chunk c+2
                 cp_async_wait<2>();  // this thread's copies of chunk c have landed
                 asm volatile("bar.sync 1, 128;" ::: "memory");  // ... and every producer's
-                const uint32_t st = wrapped & (kStages2 - 1);
+                const uint32_t st = wr_st;
                 if (WRAP) {
                     double* a = As + (size_t)st * FT * kRS2 + w_row0 * kRS2 + w_seg * 2;
 #pragma unroll
                     for (int r = 0; r < FT / 16; r++) {
                         double2* p = reinterpret_cast<double2*>(a + r * 16 * kRS2);
                         double2 v = *p;
-                        v.x = wrap_disp(v.x, rf.x);
-                        v.y = wrap_disp(v.y, rf.y);
+                        v.x = fast_wrap ? wrap_disp_fast(v.x, rf.x) : wrap_disp(v.x, rf.x);
+                        v.y = fast_wrap ? wrap_disp_fast(v.y, rf.y) : wrap_disp(v.y, rf.y);
                         *p = v;
                     }
                     if (++wr_kc == chunks) wr_kc = 0;
                 }
                 mbar_arrive2(full0 + 8 * st);  // release: this thread's stage writes are visible to waiters
-                ++wrapped;
+                if (++wr_st == (uint32_t)stages) wr_st = 0;
             }
             cp_async_wait<0>();
         }
@@ -191,11 +216,9 @@ __global__ void __launch_bounds__(384, 1)
     // =============================== MMA warps (128 threads) ===============================
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp;  // frames 16*wm .. 16*wm+15
-    uint32_t consumed = 0;
-    // padding is not computed: the last DOF tile runs only the 8-DOF column groups that hold real DOFs,
-    // the last K chunk only the 4-element k-steps that hold real coordinates (warp-uniform predicates)
-    const int nt_last = (Jreal - (jtiles - 1) * kJT2 + 7) >> 3;
-    const int ks_last = (K - (chunks - 1) * kKC2 + 3) >> 2;
+    uint32_t co_st = 0, co_round = 0;  // ring slot and round parity of the next chunk to consume
+    // DOF padding is not computed: the last DOF tile runs only the 8-DOF column groups that hold real DOFs
+    const int nt_last = keep_padding ? 8 : (Jreal - (jtiles - 1) * kJT2 + 7) >> 3;
     for (int64_t tile = tile_begin; tile < tile_end; tile++) {
         const int64_t frame0 = tile * FT;
         const int jt_lo = (int)(max(u0, tile * jtiles) - tile * jtiles);
@@ -216,39 +239,53 @@ __global__ void __launch_bounds__(384, 1)
 #pragma unroll
                     for (int nt = 0; nt < 8; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
             }
-            const uint32_t st = consumed & (kStages2 - 1);
-            mbar_wait2(full0 + 8 * st, (consumed >> 2) & 1);
+            const uint32_t st = co_st;
+            mbar_wait2(full0 + 8 * st, co_round & 1);
             const double* a_src = As + (size_t)st * FT * kRS2 + (wm * 8 * MTW + g) * kRS2 + t;
             const double* b_src = Bs + (size_t)st * kJT2 * kRS2 + g * kRS2 + t;
-            double af[2][MTW], bf[2][8];
-#pragma unroll
-            for (int mt = 0; mt < MTW; mt++) af[0][mt] = a_src[mt * 8 * kRS2];
-#pragma unroll
-            for (int nt = 0; nt < 8; nt++) bf[0][nt] = b_src[nt * 8 * kRS2];
             const int ntc = (jt == jtiles - 1) ? nt_last : 8;
-            const int ksc = (kc == chunks - 1) ? ks_last : kKC2 / 4;
+            // One copy of the chunk's MMA loop per number of live 8-DOF column groups (the last DOF tile skips
+            // its groups of pure padding): every copy is unrolled without predicates — a predicated DMMA costs
+            // a WARPSYNC and its issue slot.  K padding (< one 16-element chunk) is computed: zeros.
+            auto mma_chunk = [&](auto groups) {
+                constexpr int NTC = decltype(groups)::value;
+                double af[2][MTW], bf[2][NTC];
 #pragma unroll
-            for (int s = 0; s < kKC2 / 4; s++) {
-                const int cur = s & 1, nxt = cur ^ 1;
-                if (s + 1 < kKC2 / 4) {
+                for (int mt = 0; mt < MTW; mt++) af[0][mt] = a_src[mt * 8 * kRS2];
 #pragma unroll
-                    for (int mt = 0; mt < MTW; mt++) af[nxt][mt] = a_src[mt * 8 * kRS2 + 4 * (s + 1)];
+                for (int nt = 0; nt < NTC; nt++) bf[0][nt] = b_src[nt * 8 * kRS2];
 #pragma unroll
-                    for (int nt = 0; nt < 8; nt++) bf[nxt][nt] = b_src[nt * 8 * kRS2 + 4 * (s + 1)];
+                for (int s = 0; s < kKC2 / 4; s++) {
+                    const int cur = s & 1, nxt = cur ^ 1;
+                    if (s + 1 < kKC2 / 4) {
+#pragma unroll
+                        for (int mt = 0; mt < MTW; mt++) af[nxt][mt] = a_src[mt * 8 * kRS2 + 4 * (s + 1)];
+#pragma unroll
+                        for (int nt = 0; nt < NTC; nt++) bf[nxt][nt] = b_src[nt * 8 * kRS2 + 4 * (s + 1)];
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NTC; nt++)
+#pragma unroll
+                        for (int mt = 0; mt < MTW; mt++)
+                            dmma884(acc[mt][nt][0], acc[mt][nt][1], af[cur][mt], bf[cur][nt]);
                 }
-                if (s < ksc) {
-#pragma unroll
-                    for (int nt = 0; nt < 8; nt++)
-                        if (nt < ntc) {
-#pragma unroll
-                            for (int mt = 0; mt < MTW; mt++)
-                                dmma884(acc[mt][nt][0], acc[mt][nt][1], af[cur][mt], bf[cur][nt]);
-                        }
-                }
+            };
+            switch (ntc) {
+                case 8: mma_chunk(std::integral_constant<int, 8>{}); break;
+                case 7: mma_chunk(std::integral_constant<int, 7>{}); break;
+                case 6: mma_chunk(std::integral_constant<int, 6>{}); break;
+                case 5: mma_chunk(std::integral_constant<int, 5>{}); break;
+                case 4: mma_chunk(std::integral_constant<int, 4>{}); break;
+                case 3: mma_chunk(std::integral_constant<int, 3>{}); break;
+                case 2: mma_chunk(std::integral_constant<int, 2>{}); break;
+                default: mma_chunk(std::integral_constant<int, 1>{}); break;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive2(empty0 + 8 * st);  // stage may be refilled
-            ++consumed;
+            if (++co_st == (uint32_t)stages) {
+                co_st = 0;
+                ++co_round;
+            }
             const bool last_chunk = (kc == chunks - 1);
             const int jt_now = jt;
             if (++kc == chunks) {

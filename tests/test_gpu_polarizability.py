@@ -250,3 +250,26 @@ def test_c5_llzo_supercell_1536_atoms():
     assert rel_err(got[sel], want) <= ALPHA_RTOL
     info = model.path_info()
     assert info["num_atoms"] == 1536 and info["affine_dofs"] + info["dense_dofs"] == 4600
+
+
+@pytest.mark.parametrize("variant", [0, 64, 80, 3])
+@pytest.mark.parametrize("structure,offset", [("STO", 0), ("STO", 1), ("TiO2", 0), ("TiO2", 1)])
+def test_dense_row_alignment_and_variants(structure, offset, variant):
+    """Row alignments of the dense producers (odd row lengths — STO, 3N = 405 — and views that start on an
+    odd element take the 8-byte copy path) against the oracle, for the A/B variants of the kernel
+    (rn_debug_set_dense_config: automatic ring depth, 4 and 5 slots, branchy wrap + computed padding)."""
+    hook = _lib.lib().rn_debug_set_dense_config
+    frames = 777
+    state = synthetic.make_model(structure, "cubic", masked_fraction=0.05, seed=11)
+    positions = synthetic.make_trajectory(structure, frames, seed=5, lattice_hops=True)
+    want = ora.calc_polarizabilities(oracle_model(state), positions)
+    flat = torch.zeros(positions.size + 2, dtype=torch.float64, device="cuda:0")
+    view = flat[offset:offset + positions.size].view(positions.shape)
+    view.copy_(torch.from_numpy(positions))
+    assert view.data_ptr() % 16 == 8 * offset
+    hook(4, variant)
+    try:
+        got = rb.InterpolationModel(state).calc_polarizabilities(view).cpu().numpy()
+    finally:
+        hook(4, 0)
+    assert rel_err(got, want) <= ALPHA_RTOL

@@ -129,6 +129,19 @@ int rn_calc_polarizabilities_host_routed(const rn_model* model, const double* h_
                                          double* const* peer_series, int world, int64_t first_frame,
                                          int64_t period, int64_t width, int64_t chunk_frames,
                                          void* stream);
+/* The routed evaluation in two phases, for a schedule that overlaps the spectrum stage's (NVLink-bound)
+ * pack with the (HBM-bound) evaluation: phase 0 evaluates the frames n with (n mod 2*stripe) < stripe + 16
+ * — every row the packs of phase 0 read (rn_spectrum_dist_pack, rn_spectrum_dist_stripe) — phase 1 the
+ * others; each phase is ONE launch whose tiles map onto the selected frames.  Needs the TMA affine path
+ * (a purely linear model, 16-byte aligned rows) and blocks that start and end on multiples of 16 frames:
+ * rn_routed_phases_supported() says whether a model / block qualifies (else RN_ERR_UNSUPPORTED). */
+int rn_routed_phases_supported(const rn_model* model, const double* d_positions, int64_t num_frames,
+                               int64_t first_frame, int64_t stripe);
+int rn_calc_polarizabilities_routed_phase(const rn_model* model, const double* d_positions,
+                                          int64_t num_frames, double* d_alpha,
+                                          double* const* peer_series, int world, int64_t first_frame,
+                                          int64_t period, int64_t width, int64_t stripe, int phase,
+                                          void* stream);
 
 /* Mask sweeps: num_models models of ONE structure — in practice the
  * get_masked_model copies of a model (pmodel/_interpolation.py:697-708; ARTModel.get_dof_indexes,
@@ -188,8 +201,8 @@ int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, double timeste
  *      exactly what rn_md_spectrum returns.
  * The caller separates the steps with a cross-rank barrier (the buffers are peer-mapped device memory,
  * e.g. symmetric memory over NVLink) and provides, per rank, a work buffer, a receive buffer and a
- * spectrum buffer of rn_spectrum_dist_sizes bytes (the spectrum buffer starts with 8 doubles: the series
- * energy shares of the ranks, stored to every destination by step 2).  All ranks of the world call every
+ * spectrum buffer of rn_spectrum_dist_sizes bytes (the spectrum buffer starts with 16 doubles: the series
+ * energy shares of the ranks and pack phases, stored to every destination by step 2).  All ranks of the world call every
  * step; for spectator ranks (rank >= G) steps 2-4 return immediately.  Steps 2 and 3 take `seq`: -1
  * handles the three packed sequences in one go; 0, 1, 2 handle one sequence, so that a caller can
  * pipeline them on several streams (the NVLink-bound stores of one sequence overlap the transform of
@@ -202,8 +215,12 @@ int rn_spectrum_plan_info(const rn_spectrum_plan* plan, int64_t info[8]);
 int rn_spectrum_dist_sizes(const rn_spectrum_plan* plan, int64_t* work_bytes, int64_t* recv_bytes,
                            int64_t* spectrum_bytes);
 int rn_spectrum_dist_route(const rn_spectrum_plan* plan, int64_t* period, int64_t* width);
+/* phase: -1 packs the rank's whole block of n'; 0 / 1 pack the first / second half (rn_spectrum_dist_stripe
+ * elements each) — phase 0 reads only rows that rn_calc_polarizabilities_routed_phase(..., phase 0) stores, so
+ * it can run (on a second stream) while phase 1 of the evaluation is still streaming frames. */
+int rn_spectrum_dist_stripe(const rn_spectrum_plan* plan, int64_t* stripe);
 int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_series, double* const* peer_work,
-                          double* const* dest_spectrum, int num_dest, int seq, void* stream);
+                          double* const* dest_spectrum, int num_dest, int seq, int phase, void* stream);
 int rn_spectrum_dist_transform(rn_spectrum_plan* plan, double* d_work, double* const* peer_recv,
                                int seq, void* stream);
 int rn_spectrum_dist_final(rn_spectrum_plan* plan, const double* d_recv, const double* d_spectrum,

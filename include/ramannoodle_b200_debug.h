@@ -21,6 +21,9 @@ void rn_debug_force_generic_affine(int on);
 void rn_debug_set_affine_config(int mt, int stages);
 /* dense kernel generation: 1 = first, 3 = warp-specialised + Horner epilogue, 4 = chained-DMMA epilogue */
 void rn_debug_set_dense_config(int version, int variant);  /* variant (generation 4): bit 0 = one-DADD wrap with a branch in the producers, bit 1 = DOF padding computed, bits 4-7 = ring slots (4..7, 0 = automatic) */
+/* local 16-frame tiles that phase 0 / 1 of rn_calc_polarizabilities_routed_phase evaluates, in launch order (host only) */
+int64_t rn_debug_phase_tiles(int64_t num_frames, int64_t first_frame, int64_t stripe, int phase, int64_t* tiles,
+                             int64_t capacity);
 /* unit-balanced dense schedule: 0 = never, 1 = automatic, 2 = always */
 void rn_debug_set_dense_split(int mode);
 /* mask sweeps: fused sweep kernels on/off; shortest run of linear models worth fusing (2..4) */

@@ -44,6 +44,12 @@ PROTOTYPES = {
     "rn_calc_polarizabilities_routed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "rn_routed_phases_supported": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                                  ctypes.c_int64]),
+    "rn_calc_polarizabilities_routed_phase": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                             ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
     "rn_calc_polarizabilities_host_routed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
@@ -60,8 +66,9 @@ PROTOTYPES = {
     "rn_spectrum_plan_info": (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
     "rn_spectrum_dist_sizes": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, c_int64_p, c_int64_p]),
     "rn_spectrum_dist_route": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, c_int64_p]),
+    "rn_spectrum_dist_stripe": (ctypes.c_int, [ctypes.c_void_p, c_int64_p]),
     "rn_spectrum_dist_pack": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                             ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "rn_spectrum_dist_transform": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                                   ctypes.c_void_p]),
     "rn_spectrum_dist_final": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -101,6 +108,8 @@ DEBUG_PROTOTYPES = {
     "rn_debug_force_generic_affine": (None, [ctypes.c_int]),
     "rn_debug_set_affine_config": (None, [ctypes.c_int, ctypes.c_int]),
     "rn_debug_set_dense_config": (None, [ctypes.c_int, ctypes.c_int]),
+    "rn_debug_phase_tiles": (ctypes.c_int64, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_int64_p,
+                                              ctypes.c_int64]),
     "rn_debug_set_dense_split": (None, [ctypes.c_int]),
     "rn_debug_set_sweep_fused": (None, [ctypes.c_int]),
     "rn_debug_set_sweep_min_run": (None, [ctypes.c_int]),

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdint>
@@ -108,13 +109,103 @@ namespace rn {
 //     for ranks that own nothing); row n (global index first_frame + local row) goes to the ranks
 //     owner(n) and owner(n-1), owner(n) = (n mod 2^log2_period) >> log2_width — the rank whose spectrum
 //     stage consumes the difference signal n needs rows n and n+1 (rn_spectrum_dist_route).
+// A subset of the local frames for one launch (pipelined multi-GPU schedule: the rows one half of the
+// spectrum stage's pack needs are evaluated first, so that the pack can overlap the evaluation of the rest).
+// In units of tiles of the kernel's frames-per-tile: local tile t has the global number g = tile0 + t; the
+// launch processes the tiles with lo <= g mod period < lo + width, in increasing order.
+struct TileSelect {
+    int64_t period;  // 0: every tile
+    int64_t lo, width;
+    int64_t x0;      // tile0 mod period
+    int64_t c0;      // selected tiles before the first period boundary
+    int64_t count;   // selected tiles in all
+};
+
 struct AlphaPeers {
     double* ptr[8];
     int count;
     int log2_period;
     int log2_width;
     int64_t first_frame;
+    int64_t sel_stripe;  // > 0: evaluate one phase only (rn_calc_polarizabilities_routed_phase)
+    int sel_phase;
 };
+
+// local tile of the j-th selected one
+__host__ __device__ inline int64_t select_tile(const TileSelect& S, int64_t j) {
+    if (S.period == 0) return j;
+    const int64_t first = S.x0 > S.lo ? S.x0 : S.lo;
+    if (j < S.c0) return first - S.x0 + j;
+    j -= S.c0;
+    return (1 + j / S.width) * S.period + S.lo + (j % S.width) - S.x0;
+}
+
+// The same walk without divisions in the loop: a CTA visits the selected tiles j, j + step, j + 2 step, ...
+struct TileCursor {
+    int64_t j;       // index among the selected tiles
+    int64_t k, r;    // j >= c0: period number (>= 1) and offset inside the window
+};
+__host__ __device__ inline void cursor_set(const TileSelect& S, int64_t j, TileCursor& c) {
+    c.j = j;
+    c.k = 0;
+    c.r = 0;
+    if (S.period && j >= S.c0) {
+        c.k = 1 + (j - S.c0) / S.width;
+        c.r = (j - S.c0) % S.width;
+    }
+}
+__host__ __device__ inline void cursor_advance(const TileSelect& S, int64_t step, TileCursor& c) {
+    const int64_t before = c.j;
+    c.j += step;
+    if (!S.period || c.j < S.c0) return;
+    if (before < S.c0) {
+        c.k = 1;
+        c.r = c.j - S.c0;
+    } else {
+        c.r += step;
+    }
+    while (c.r >= S.width) {
+        c.r -= S.width;
+        c.k++;
+    }
+}
+__host__ __device__ inline int64_t cursor_tile(const TileSelect& S, const TileCursor& c) {
+    if (S.period == 0) return c.j;
+    if (c.j < S.c0) return (S.x0 > S.lo ? S.x0 : S.lo) - S.x0 + c.j;
+    return c.k * S.period + S.lo + c.r - S.x0;
+}
+
+inline TileSelect all_tiles() {
+    TileSelect S;
+    S.period = S.lo = S.width = S.x0 = S.c0 = S.count = 0;
+    return S;
+}
+
+// selection of the tiles lo <= g mod period < lo + width among local tiles [0, num_tiles), g = tile0 + t
+inline TileSelect make_tile_select(int64_t tile0, int64_t num_tiles, int64_t period, int64_t lo, int64_t width) {
+    TileSelect S;
+    S.period = period;
+    S.lo = lo;
+    S.width = width;
+    S.x0 = tile0 % period;
+    const int64_t first = S.x0 > lo ? S.x0 : lo;
+    const int64_t in_first = std::max<int64_t>(0, std::min(lo + width, S.x0 + num_tiles) - first);
+    S.c0 = in_first;
+    int64_t count = in_first;
+    const int64_t end = S.x0 + num_tiles;  // one past the last local tile, counted from the period start
+    for (int64_t k = 1; k * period < end; k++)
+        count += std::max<int64_t>(0, std::min(k * period + lo + width, end) - (k * period + lo));
+    S.count = count;
+    return S;
+}
+
+// the tiles (of `rows` frames, a divisor of 16) of one phase of the pipelined schedule: phase 0 = frames n with
+// (n mod 2 stripe) < stripe + 16, phase 1 = the others
+inline TileSelect phase_tiles(int64_t first_frame, int64_t num_frames, int64_t stripe, int phase, int rows) {
+    const int64_t edge = (stripe + 16) / rows, period = 2 * stripe / rows;
+    return phase == 0 ? make_tile_select(first_frame / rows, num_frames / rows, period, 0, edge)
+                      : make_tile_select(first_frame / rows, num_frames / rows, period, edge, period - edge);
+}
 
 // bit r set: rows [local_row, local_row + rows) go to ptr[r] (rows <= 2^log2_width: at most two owners)
 __host__ __device__ inline uint32_t alpha_peer_mask(const AlphaPeers& P, int64_t local_row, int rows) {
@@ -131,6 +222,8 @@ inline AlphaPeers no_peers() {
     p.log2_period = -1;
     p.log2_width = 0;
     p.first_frame = 0;
+    p.sel_stripe = 0;
+    p.sel_phase = 0;
     return p;
 }
 // offset (doubles) of local row `local_row` in destination r

@@ -164,8 +164,11 @@ __device__ __forceinline__ double2 tw_global(const Twiddles& T, uint32_t m) {
 // c = M mod Lh; ownership of m' is therefore MIRROR-SYMMETRIC, so that one rank holds both members of
 // every pair and finishes the pair's intensity by itself.  With u = (2 m' - c) mod 2 Lh and
 // a = min(u, 2 Lh - u) (the doubled circular distance from c/2, the same for m' and its mirror image),
-// the owner is min(a / w, G - 1), w = Lh / G; inside the owner's slice (seq, source rank) — w + 2 slots —
-// element a sits at (a - owner w) / 2 on the side u <= Lh and w/2 + 1 slots further on the other side.
+// the owner is min(a / w, G - 1), w = Lh / G.  The owner's slice (seq, source rank) has two halves of
+// w/2 + 64 slots: residues on the side u <= Lh ascend from a 32-aligned origin, the mirror side descends
+// from a top that is 31 (mod 32) — either way a run of 32 consecutive residues that starts at a multiple of
+// 32 lands in one aligned 512-byte block of the peer's buffer (unaligned runs cost the NVLink stores of the
+// last pass a third of their rate).
 struct PeerOut {
     double2* ptr[8];
     int log2w;
@@ -175,7 +178,18 @@ struct PeerOut {
     int64_t c;  // M mod Lh
 };
 
-// owner of residue m1 and its slot within one (seq, source rank) slice of w + 2 slots
+__host__ __device__ __forceinline__ int64_t mirror_half_slots(int log2w) { return ((int64_t)1 << (log2w - 1)) + 64; }
+
+// origin of owner o's ascending half and top of its descending half (residues)
+__device__ __forceinline__ void mirror_arcs(int o, int64_t c, int log2lh, int log2w, int64_t* near_origin,
+                                            int64_t* far_top) {
+    const int64_t lh = (int64_t)1 << log2lh;
+    const int64_t a0 = ((int64_t)o << log2w) + (c & 1);  // smallest doubled distance this owner holds
+    *near_origin = (((c + a0) >> 1) & (lh - 1)) & ~(int64_t)31;
+    *far_top = (((2 * lh + c - a0) >> 1) & (lh - 1)) | 31;
+}
+
+// owner of residue m1 and its slot within one (seq, source rank) slice of 2 * mirror_half_slots() slots
 __device__ __forceinline__ void mirror_owner(int64_t m1, int64_t c, int log2lh, int log2w, int world, int* owner,
                                              int64_t* slot) {
     const int64_t lh = (int64_t)1 << log2lh;
@@ -184,8 +198,10 @@ __device__ __forceinline__ void mirror_owner(int64_t m1, int64_t c, int log2lh, 
     const bool far_side = u > lh;
     const int64_t a = far_side ? 2 * lh - u : u;
     const int o = min((int)(a >> log2w), world - 1);
+    int64_t near_origin, far_top;
+    mirror_arcs(o, c, log2lh, log2w, &near_origin, &far_top);
     *owner = o;
-    *slot = ((a - ((int64_t)o << log2w)) >> 1) + (far_side ? ((int64_t)1 << (log2w - 1)) + 1 : 0);
+    *slot = far_side ? mirror_half_slots(log2w) + ((far_top - m1) & (lh - 1)) : ((m1 - near_origin) & (lh - 1));
 }
 
 struct OutSpec {
@@ -204,7 +220,7 @@ __device__ __forceinline__ void store_out(const OutSpec& out, double2* plain, in
         int owner;
         int64_t slot;
         mirror_owner(m, out.peers.c, out.peers.log2lh, out.peers.log2w, out.peers.world, &owner, &slot);
-        const int64_t stride = ((int64_t)1 << out.peers.log2w) + 2;
+        const int64_t stride = 2 * mirror_half_slots(out.peers.log2w);
         out.peers.ptr[owner][(int64_t)(seq * out.peers.world + out.peers.rank) * stride + slot] = v;
     }
 }

@@ -95,7 +95,7 @@ template <int KP, int MT, int STAGES, bool WRAP>
 __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 1)
     affine_tma_kernel(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ G,
                       int64_t num_frames, int K, int row_stride, int stage_doubles, Alpha0 a0,
-                      double* __restrict__ alpha, AlphaPeers peers, int peers_bulk) {
+                      double* __restrict__ alpha, AlphaPeers peers, int peers_bulk, TileSelect sel) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ROWS = 8 * MT;
     constexpr int RED = kAffineWarps * ROWS * kRedStride;  // doubles per reduction buffer
@@ -104,16 +104,22 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
     double* red = stages + STAGES * stage_doubles + slack;
     double* tab_ref = red + 2 * RED;       // [kAffineWarps*8*KP] wrapped reference positions
     double* tab_g9 = tab_ref + slack;      // [kAffineWarps*8*KP] column 8 of G
-    double* outbuf = tab_g9 + slack;       // [2][ROWS*9] finished rows staged for the bulk stores to the peers
+    // [2][ROWS*9] finished rows staged for the bulk stores to the peers.  (A deeper ring — 8 or 16 tiles with
+    // cp.async.bulk.wait_group.read 6 / 14 — was measured on 4 GPUs: 0.87 / 0.95 ms against 0.85 ms; more bulk
+    // stores in flight per CTA make the kernel slower, not more tolerant of NVLink bursts.)
+    double* outbuf = tab_g9 + slack;
     uint64_t* bars = reinterpret_cast<uint64_t*>(outbuf + 2 * ROWS * 9);
     const uint32_t full0 = smem_u32(bars);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t num_tiles = (num_frames + ROWS - 1) / ROWS;
+    // the tiles of this launch: all of them, or the selection of one phase of the pipelined schedule (then
+    // num_frames is a multiple of ROWS).  Two cursors walk this CTA's tiles: the one computed on, and the one
+    // being fetched STAGES visits ahead.
+    const int64_t num_tiles = sel.period ? sel.count : (num_frames + ROWS - 1) / ROWS;
     const uint32_t row_bytes = (uint32_t)K * 8u;
 
     auto issue_tile = [&](int64_t tile, int s) {
-        const int64_t frame0 = tile * ROWS;
+        const int64_t frame0 = select_tile(sel, tile) * ROWS;  // (prologue only: a division per call)
         const int rows = (int)min((int64_t)ROWS, num_frames - frame0);
         mbar_arrive_expect_tx(full0 + 8 * s, row_bytes * rows);
         const uint32_t dst0 = smem_u32(stages + (size_t)s * stage_doubles);
@@ -156,11 +162,16 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
     double* myred = red + ((size_t)warp * ROWS + g) * kRedStride;
 
     int64_t i = 0;
-    int64_t pending_tile = -1;  // tile whose rows sit in outbuf waiting for their bulk stores
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
+    int64_t pending_row0 = -1;  // first row of the tile that sits in outbuf waiting for its bulk stores
+    TileCursor here, ahead;
+    cursor_set(sel, blockIdx.x, here);
+    cursor_set(sel, blockIdx.x + (int64_t)STAGES * gridDim.x, ahead);
+    for (int64_t tile = blockIdx.x; tile < num_tiles;
+         tile += gridDim.x, i++, cursor_advance(sel, gridDim.x, here), cursor_advance(sel, gridDim.x, ahead)) {
         const int s = (int)(i % STAGES);
+        const int64_t tile_row0 = cursor_tile(sel, here) * ROWS;
         // full tiles go to the peers as bulk stores; a partial last tile uses plain stores
-        const bool stage_rows = peers_bulk && (tile * ROWS + ROWS <= num_frames);
+        const bool stage_rows = peers_bulk && (tile_row0 + ROWS <= num_frames);
         mbar_wait(full0 + 8 * s, (uint32_t)(i / STAGES) & 1);
         const double* base = stages + (size_t)s * stage_doubles + rowoff;
         // independent accumulator chains (2 per 8-frame group): one DMMA/DFMA dependency chain
@@ -202,12 +213,12 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
             if (t == 0) slot[(size_t)m * 8 * kRedStride + 8] = a9s;
         }
         __syncthreads();  // partials visible; every warp is done reading stage s
-        if (peers_bulk && threadIdx.x == 32 && pending_tile >= 0) {
+        if (peers_bulk && threadIdx.x == 32 && pending_row0 >= 0) {
             // fused all-gather: the previous tile's finished rows (staged in smem, complete since this
             // barrier) go to every peer GPU as one TMA bulk store each (UBLKCP S2G over NVLink)
             const uint32_t src = smem_u32(outbuf + (size_t)((i - 1) & 1) * ROWS * 9);
-            const uint32_t mask = alpha_peer_mask(peers, pending_tile * ROWS, ROWS);
-            const int64_t off = alpha_peer_offset(peers, pending_tile * ROWS);
+            const uint32_t mask = alpha_peer_mask(peers, pending_row0, ROWS);
+            const int64_t off = alpha_peer_offset(peers, pending_row0);
             for (int p = 0; p < peers.count; p++)
                 if (((mask >> p) & 1u) && peers.ptr[p])
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(peers.ptr[p] + off),
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
             // refill stage s: thread 0 arms the barrier, lane 0 of warp w copies rows w, w+8, ...
             const int64_t next = tile + (int64_t)STAGES * gridDim.x;
             if (next < num_tiles && lane == 0) {
-                const int64_t frame0 = next * ROWS;
+                const int64_t frame0 = cursor_tile(sel, ahead) * ROWS;
                 const int rows = (int)min((int64_t)ROWS, num_frames - frame0);
                 if (warp == 0) mbar_arrive_expect_tx(full0 + 8 * s, row_bytes * rows);
                 const uint32_t dst0 = smem_u32(stages + (size_t)s * stage_doubles);
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
             double sum = 0;
 #pragma unroll
             for (int w = 0; w < kAffineWarps; w++) sum += r[(size_t)w * ROWS * kRedStride];
-            const int64_t frame = tile * ROWS + f;
+            const int64_t frame = tile_row0 + f;
             const double value = sum + a0.v[q];
             if (frame < num_frames) alpha[frame * 9 + q] = value;
             if (stage_rows) {
@@ -253,14 +264,14 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
             // the staging buffer written two tiles from now must not be read by a bulk store any more
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        pending_tile = stage_rows ? tile : -1;
+        pending_row0 = stage_rows ? tile_row0 : -1;
     }
     if (peers_bulk) {
         __syncthreads();
-        if (threadIdx.x == 32 && pending_tile >= 0) {
+        if (threadIdx.x == 32 && pending_row0 >= 0) {
             const uint32_t src = smem_u32(outbuf + (size_t)((i - 1) & 1) * ROWS * 9);
-            const uint32_t mask = alpha_peer_mask(peers, pending_tile * ROWS, ROWS);
-            const int64_t off = alpha_peer_offset(peers, pending_tile * ROWS);
+            const uint32_t mask = alpha_peer_mask(peers, pending_row0, ROWS);
+            const int64_t off = alpha_peer_offset(peers, pending_row0);
             for (int p = 0; p < peers.count; p++)
                 if (((mask >> p) & 1u) && peers.ptr[p])
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(peers.ptr[p] + off),
@@ -280,7 +291,10 @@ static int launch_affine_tma_cfg(const rn_model* m, const double* d_in, int64_t 
     const int K = (int)m->dim;
     const AffineSmemLayout L = affine_layout(K, KP, MT, STAGES);
     if (L.bytes > 227 * 1024) return 1;  // does not fit: caller tries a smaller configuration
-    const int64_t tiles = (frames + 8 * MT - 1) / (8 * MT);
+    const TileSelect sel = peers.sel_stripe > 0 ? phase_tiles(peers.first_frame, frames, peers.sel_stripe, peers.sel_phase, 8 * MT)
+                                                : all_tiles();
+    const int64_t tiles = sel.period ? sel.count : (frames + 8 * MT - 1) / (8 * MT);
+    if (tiles == 0) return RN_OK;
     const double* ref = WRAP ? m->d_ref_wrapped : m->d_zero_ref;
     const double* G = WRAP ? m->d_g_frac : m->d_g_cart;
     auto kern = affine_tma_kernel<KP, MT, STAGES, WRAP>;
@@ -294,8 +308,9 @@ static int launch_affine_tma_cfg(const rn_model* m, const double* d_in, int64_t 
     for (int p = 0; p < peers.count; p++)
         if (peers.ptr[p] && reinterpret_cast<uintptr_t>(peers.ptr[p]) % 16 != 0) peers_bulk = 0;
     if (peers.log2_period >= 0 && (peers.first_frame * 72) % 16 != 0) peers_bulk = 0;
+    // (plain st.global to the peers instead of bulk stores: 0.96 ms against 0.85 ms on 4 GPUs)
     kern<<<grid, kAffineWarps * 32, L.bytes, stream>>>(d_in, ref, G, frames, K, L.row_stride, L.stage_doubles, a0,
-                                                       d_alpha, peers, peers_bulk);
+                                                       d_alpha, peers, peers_bulk, sel);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
     return RN_OK;
@@ -376,6 +391,10 @@ int launch_affine(const rn_model* m, const double* d_in, bool wrap, int64_t num_
             rc = RN_OK;
         }
         if (rc != RN_OK) return rc;
+    }
+    if (fused.sel_stripe > 0 && tma_frames != num_frames) {
+        set_error("a frame selection (pipelined multi-GPU schedule) needs the TMA affine kernel");
+        return RN_ERR_UNSUPPORTED;
     }
     // the TMA kernel stores to the peers itself; the generic fallback does not
     if (peers_done) *peers_done = (tma_frames == num_frames);
@@ -712,6 +731,39 @@ extern "C" int rn_calc_polarizabilities_routed(const rn_model* model, const doub
     return eval_common(model, d_positions, true, num_frames, d_alpha, stream, &peers);
 }
 
+// One phase of the pipelined schedule: the frames n of the block with (n mod 2 stripe) < stripe + 16 (phase 0:
+// everything the packs of the stripes' first halves read, their rows n + 1 included) or the others (phase 1).
+static bool routed_phases_ok(const rn_model* model, const double* d_positions, int64_t num_frames, int64_t first_frame,
+                             int64_t stripe) {
+    if (!model || model->num_dofs == 0 || model->num_dense > 0 || model->num_linear == 0 || model->affine_kp <= 0) return false;
+    if (g_force_generic_affine.load(std::memory_order_relaxed)) return false;
+    if (reinterpret_cast<uintptr_t>(d_positions) % 16 != 0 || model->dim % 2 != 0) return false;
+    return stripe >= 1024 && (stripe & (stripe - 1)) == 0 && num_frames % 16 == 0 && first_frame % 16 == 0 &&
+           num_frames >= 16;
+}
+
+extern "C" int rn_routed_phases_supported(const rn_model* model, const double* d_positions, int64_t num_frames,
+                                          int64_t first_frame, int64_t stripe) {
+    return routed_phases_ok(model, d_positions, num_frames, first_frame, stripe) ? 1 : 0;
+}
+
+extern "C" int rn_calc_polarizabilities_routed_phase(const rn_model* model, const double* d_positions,
+                                                     int64_t num_frames, double* d_alpha, double* const* peer_series,
+                                                     int world, int64_t first_frame, int64_t period, int64_t width,
+                                                     int64_t stripe, int phase, void* stream) {
+    RN_CHECK_ARG(phase == 0 || phase == 1, "phase must be 0 or 1");
+    if (!routed_phases_ok(model, d_positions, num_frames, first_frame, stripe)) {
+        set_error("this model / trajectory block cannot be evaluated in phases (rn_routed_phases_supported)");
+        return RN_ERR_UNSUPPORTED;
+    }
+    AlphaPeers peers;
+    int rc = make_routed_peers(peer_series, world, first_frame, period, width, &peers);
+    if (rc != RN_OK) return rc;
+    peers.sel_stripe = stripe;
+    peers.sel_phase = phase;
+    return eval_common(model, d_positions, true, num_frames, d_alpha, stream, &peers);
+}
+
 extern "C" int rn_calc_polarizabilities(const rn_model* model, const double* d_positions, int64_t num_frames,
                                         double* d_alpha, void* stream) {
     return eval_common(model, d_positions, true, num_frames, d_alpha, stream);
@@ -720,6 +772,23 @@ extern "C" int rn_calc_polarizabilities(const rn_model* model, const double* d_p
 extern "C" int rn_get_polarizability(const rn_model* model, const double* d_cart_displacements, int64_t num_frames,
                                      double* d_alpha, void* stream) {
     return eval_common(model, d_cart_displacements, false, num_frames, d_alpha, stream);
+}
+
+// Test hook: the local 16-frame tiles one phase of rn_calc_polarizabilities_routed_phase evaluates, in launch order
+// (host arithmetic only; returns their number, fills at most `capacity`).
+extern "C" int64_t rn_debug_phase_tiles(int64_t num_frames, int64_t first_frame, int64_t stripe, int phase,
+                                        int64_t* tiles, int64_t capacity) {
+    // (walked with the cursor the kernel uses, from two starting points like two CTAs of a grid of 2)
+    const TileSelect sel = phase_tiles(first_frame, num_frames, stripe, phase, 16);
+    for (int64_t start = 0; start < 2; start++) {
+        TileCursor c;
+        cursor_set(sel, start, c);
+        for (int64_t j = start; j < sel.count; j += 2, cursor_advance(sel, 2, c)) {
+            if (cursor_tile(sel, c) != select_tile(sel, j)) return -1;
+            if (j < capacity) tiles[j] = cursor_tile(sel, c);
+        }
+    }
+    return sel.count;
 }
 
 // Test hook (include/ramannoodle_b200_debug.h): route the affine term through the generic kernel.

@@ -98,6 +98,9 @@ struct PackParams {
     double* share[8];      // shared transform: the sum also goes to slot `share_slot` of these spectrum buffers
     int num_share;
     int share_slot;
+    int zero_slot;         // >= 0: this slot is cleared (the other phase's share when the pack is not split)
+    int log2_stripe;       // >= 0: this launch packs one half of every block of 2^(log2_stripe+1) n' ...
+    int phase;             // ... the first (0) or the second (1)
     Twiddles tw;
 };
 
@@ -136,7 +139,10 @@ __device__ __forceinline__ void publish_energy(double block_total, double* epart
         epart[gridDim.x] = total;
         *ticket = 0;
         if (share)  // this rank's share of the series energy, to every rank that forms intensities
-            for (int d = 0; d < share->num_share; d++) share->share[d][share->share_slot] = total;
+            for (int d = 0; d < share->num_share; d++) {
+                share->share[d][share->share_slot] = total;
+                if (share->zero_slot >= 0) share->share[d][share->zero_slot] = 0.0;
+            }
     }
 }
 
@@ -147,7 +153,11 @@ __global__ void __launch_bounds__(kPackThreads) pack_alpha_kernel(const __grid_c
     constexpr int GH = G > 1 ? G / 2 : 1;
     __shared__ __align__(16) double rows[(kPackThreads + 1) * 9 + 1];
     __shared__ double red[kPackThreads / 32];
-    const int64_t n0 = P.begin + (int64_t)blockIdx.x * kPackThreads;
+    int64_t n0 = P.begin + (int64_t)blockIdx.x * kPackThreads;
+    if (P.log2_stripe >= 0) {  // stripes are multiples of the block size: a block stays inside one stripe
+        const int64_t idx = (int64_t)blockIdx.x * kPackThreads, stripe = (int64_t)1 << P.log2_stripe;
+        n0 = P.begin + ((idx >> P.log2_stripe) << (P.log2_stripe + 1)) + (idx & (stripe - 1)) + P.phase * stripe;
+    }
     const int64_t n1 = n0 + threadIdx.x;  // n'
     double2 a[GH][3];
     double energy = 0.0;
@@ -296,10 +306,10 @@ __device__ __forceinline__ double corrected(double inten, double wn, const Spect
 
 // ---- final stage of a shared transform: y[q Lh + m'] from the G residues for a mirror pair of m', the
 // pair's finished intensities I[k] = (P[k] + P[M-k]) / (4 L^2) + E/2 (corrections included) to every rank
-constexpr int kSpecHeader = 8;  // spectrum buffer: energy shares of ranks 0..7, then the intensities
+constexpr int kSpecHeader = 16;  // spectrum buffer: energy shares (rank + 8 * pack phase), then the intensities
 
 struct FinalParams {
-    const double2* recv;  // (3, G, w + 2) slices z_r[m'] of the residues this rank owns (fft::mirror_owner)
+    const double2* recv;  // (3, G, w + 128) slices z_r[m'] of the residues this rank owns (fft::mirror_owner)
     int64_t M, Lh, c;     // c = M mod Lh
     int log2w, log2lh;
     int rank;
@@ -324,13 +334,14 @@ __global__ void __launch_bounds__(256) final_dist_kernel(const __grid_constant__
     if (valid) {
         double energy = 0.0;
 #pragma unroll
-        for (int r = 0; r < G; r++) energy += P.shares[r];
+        for (int r = 0; r < G; r++) energy += P.shares[r] + P.shares[8 + r];
         const double econst = 0.5 * energy;
         const bool self_paired = (a == 0 || a == P.Lh);
-        const int64_t stride = w + 2;
-        int64_t m1[2];
+        const int64_t stride = 2 * fft::mirror_half_slots(P.log2w);
+        int64_t m1[2], near_origin, far_top;
         m1[0] = ((a + P.c) >> 1) & (P.Lh - 1);
         m1[1] = ((2 * P.Lh + P.c - a) >> 1) & (P.Lh - 1);
+        fft::mirror_arcs(P.rank, P.c, P.log2lh, P.log2w, &near_origin, &far_top);
         double power[2][GH];
 #pragma unroll
         for (int side = 0; side < 2; side++) {
@@ -343,7 +354,8 @@ __global__ void __launch_bounds__(256) final_dist_kernel(const __grid_constant__
             }
             double2 w1 = fft::tw_global(P.tw, (uint32_t)m1[side]);
             w1.y = -w1.y;
-            const int64_t slot = local + (side ? half + 1 : 0);
+            const int64_t slot = side ? fft::mirror_half_slots(P.log2w) + ((far_top - m1[1]) & (P.Lh - 1))
+                                      : ((m1[0] - near_origin) & (P.Lh - 1));
 #pragma unroll
             for (int s = 0; s < 3; s++) {
                 double2 z[G];
@@ -621,8 +633,8 @@ static int create_plan(int64_t num_frames, int device, int world, int rank, rn_s
     alloc((void**)&p->d_H, sizeof(double2) * p->Lh);
     alloc((void**)&p->d_work, sizeof(double2) * (group > 1 ? 1 : 3) * p->Lh);
     if (group == 1) alloc((void**)&p->d_power, sizeof(double) * 3 * M);
-    alloc((void**)&p->d_epart, sizeof(double) * (p->pack_blocks + 1));
-    alloc((void**)&p->d_ticket, sizeof(unsigned int));
+    alloc((void**)&p->d_epart, sizeof(double) * 2 * (p->pack_blocks + 1));  // two pack phases
+    alloc((void**)&p->d_ticket, 2 * sizeof(unsigned int));
     if (err != cudaSuccess) {
         set_error("cudaMalloc failed while creating a spectrum plan for %lld frames: %s", (long long)num_frames,
                   cudaGetErrorString(err));
@@ -630,7 +642,7 @@ static int create_plan(int64_t num_frames, int device, int world, int rank, rn_s
         cudaGetLastError();
         return RN_ERR_OUT_OF_MEMORY;
     }
-    cudaMemset(p->d_ticket, 0, sizeof(unsigned int));
+    cudaMemset(p->d_ticket, 0, 2 * sizeof(unsigned int));
     std::vector<double2> whi((size_t)n_hi), wlo((size_t)n_lo), wsub((size_t)kE);
     for (int64_t a = 0; a < n_hi; a++) whi[(size_t)a] = unit_root(a << p->split, p->L);
     for (int64_t b = 0; b < n_lo; b++) wlo[(size_t)b] = unit_root(b, p->L);
@@ -744,6 +756,9 @@ extern "C" int rn_md_spectrum(rn_spectrum_plan* plan, const double* d_alpha, dou
     pp.seq_sel = -1;
     pp.num_share = 0;
     pp.share_slot = 0;
+    pp.zero_slot = -1;
+    pp.log2_stripe = -1;
+    pp.phase = 0;
     for (int i = 0; i < 8; i++) pp.share[i] = nullptr;
     pp.epart = plan->d_epart;
     pp.ticket = plan->d_ticket;
@@ -788,6 +803,9 @@ extern "C" int rn_signal_spectrum(rn_spectrum_plan* plan, const double* d_signal
     pp.seq_sel = -1;
     pp.num_share = 0;
     pp.share_slot = 0;
+    pp.zero_slot = -1;
+    pp.log2_stripe = -1;
+    pp.phase = 0;
     for (int i = 0; i < 8; i++) pp.share[i] = nullptr;
     pp.epart = plan->d_epart;
     pp.ticket = plan->d_ticket;
@@ -815,8 +833,8 @@ extern "C" int rn_spectrum_dist_sizes(const rn_spectrum_plan* plan, int64_t* wor
                                       int64_t* spectrum_bytes) {
     RN_CHECK_ARG(plan && work_bytes && recv_bytes && spectrum_bytes, "null pointer");
     *work_bytes = (int64_t)sizeof(double2) * 3 * plan->Lh;
-    // 3 sequences x G residues x (Lh / G + 2) slots for the m' this rank owns (fft::mirror_owner)
-    *recv_bytes = (int64_t)sizeof(double2) * 3 * (plan->Lh + 2 * plan->world);
+    // 3 sequences x G residues x (Lh / G + 128) slots for the m' this rank owns (fft::mirror_owner)
+    *recv_bytes = (int64_t)sizeof(double2) * 3 * (plan->Lh + 128 * plan->world);
     *spectrum_bytes = (int64_t)sizeof(double) * (kSpecHeader + rn_spectrum_num_points(plan->S));
     return RN_OK;
 }
@@ -829,17 +847,32 @@ extern "C" int rn_spectrum_dist_route(const rn_spectrum_plan* plan, int64_t* per
 }
 
 template <int G>
-static int launch_pack_dist(const rn_spectrum_plan* plan, const PackParams& pp, cudaStream_t s) {
-    pack_alpha_kernel<G><<<plan->pack_blocks, kPackThreads, 0, s>>>(pp);
+static int launch_pack_dist(const rn_spectrum_plan* plan, const PackParams& pp, int blocks, cudaStream_t s) {
+    pack_alpha_kernel<G><<<blocks, kPackThreads, 0, s>>>(pp);
     RN_LAUNCHED();
     RN_CUDA(cudaGetLastError());
+    (void)plan;
+    return RN_OK;
+}
+
+// stripe of the pipelined schedule: half of the block of n' one rank packs (0: the block is too small)
+static int64_t dist_stripe(const rn_spectrum_plan* plan) {
+    const int64_t w = plan->Lh / plan->world;
+    return (plan->world > 1 && w >= 4096) ? w / 2 : 0;
+}
+
+extern "C" int rn_spectrum_dist_stripe(const rn_spectrum_plan* plan, int64_t* stripe) {
+    RN_CHECK_ARG(plan && stripe, "null pointer");
+    *stripe = dist_stripe(plan);
     return RN_OK;
 }
 
 extern "C" int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_series, double* const* peer_work,
-                                     double* const* dest_spectrum, int num_dest, int seq, void* stream) {
+                                     double* const* dest_spectrum, int num_dest, int seq, int phase, void* stream) {
     RN_CHECK_ARG(plan && d_series && peer_work && dest_spectrum, "null pointer");
     RN_CHECK_ARG(seq >= -1 && seq <= 2, "seq must be -1 (all) or 0..2");
+    RN_CHECK_ARG(phase >= -1 && phase <= 1, "phase must be -1 (whole block), 0 or 1");
+    RN_CHECK_ARG(phase < 0 || (seq < 0 && dist_stripe(plan) > 0), "a split pack handles all sequences of a large enough block");
     RN_CHECK_ARG(num_dest >= 1 && num_dest <= 8, "between 1 and 8 destinations");
     if (plan->rank >= plan->world) return RN_OK;  // spectator
     RN_CHECK_ARG(plan->world > 1, "rn_spectrum_dist_pack needs a plan from rn_spectrum_plan_create_dist with world > 1");
@@ -857,24 +890,32 @@ extern "C" int rn_spectrum_dist_pack(rn_spectrum_plan* plan, const double* d_ser
         pp.dst[r] = reinterpret_cast<double2*>(peer_work[r]);
     }
     pp.aligned16 = (reinterpret_cast<uintptr_t>(pp.src) % 16 == 0) ? 1 : 0;
-    pp.seq_sel = -1;
-    pp.num_share = 0;
-    pp.share_slot = 0;
-    for (int i = 0; i < 8; i++) pp.share[i] = nullptr;
-    pp.epart = plan->d_epart;
-    pp.ticket = plan->d_ticket;
+    // the two phases of a split pack may run concurrently: each has its own partials and ticket
+    const int second = phase == 1 ? 1 : 0;
+    pp.epart = plan->d_epart + second * (plan->pack_blocks + 1);
+    pp.ticket = plan->d_ticket + second;
     pp.tw = plan_twiddles(plan);
     pp.seq_sel = seq;
+    for (int i = 0; i < 8; i++) pp.share[i] = nullptr;
     for (int d = 0; d < num_dest; d++) {
         RN_CHECK_ARG(dest_spectrum[d] != nullptr, "null spectrum buffer pointer %d", d);
         pp.share[d] = dest_spectrum[d];
     }
     pp.num_share = num_dest;
-    pp.share_slot = plan->rank;
+    pp.share_slot = plan->rank + 8 * second;
+    pp.zero_slot = phase < 0 ? plan->rank + 8 : -1;
+    pp.log2_stripe = -1;
+    pp.phase = second;
+    int blocks = plan->pack_blocks;
+    if (phase >= 0) {
+        const int64_t stripe = dist_stripe(plan);
+        while (((int64_t)1 << (pp.log2_stripe + 1)) <= stripe) pp.log2_stripe++;
+        blocks = (int)(stripe / kPackThreads);
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (plan->world == 2) return launch_pack_dist<2>(plan, pp, s);
-    if (plan->world == 4) return launch_pack_dist<4>(plan, pp, s);
-    return launch_pack_dist<8>(plan, pp, s);
+    if (plan->world == 2) return launch_pack_dist<2>(plan, pp, blocks, s);
+    if (plan->world == 4) return launch_pack_dist<4>(plan, pp, blocks, s);
+    return launch_pack_dist<8>(plan, pp, blocks, s);
 }
 
 extern "C" int rn_spectrum_dist_transform(rn_spectrum_plan* plan, double* d_work, double* const* peer_recv,

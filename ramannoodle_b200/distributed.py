@@ -8,11 +8,14 @@ SHARED by the ranks (decimation in frequency at rank level, ``csrc/rn_spectrum.c
 
 1. the evaluation kernels store every row of the (S,3,3) series straight to the rank whose spectrum
    stage consumes it (peer stores over NVLink into symmetric memory; every row has one or two
-   destinations, so the series is never all-gathered);
+   destinations, so the series is never all-gathered).  Optionally (RN_DIST_OVERLAP=1, off by default: measured
+   slower) HBM-resident blocks of purely linear models are evaluated in two launches — first the frames the
+   first half of every rank's pack reads — with that half of the pack on a second stream under the second launch;
 2. ``pack`` (np.diff, signal packing, chirp, G-point DFT over the blocks) stores residue r into rank
    r's work buffer; 3. every rank runs its local length-L/G convolution and stores the result to the
-   ranks owning the output blocks; 4. ``final`` finishes its block and stores P = sum |y|^2 to every
-   rank; 5. every rank forms the intensities.  Device-side barriers separate the steps; there is no
+   ranks owning the output residues (mirror-symmetric ownership: the owner of bin m also owns bin M - m);
+   4. ``final`` finishes the intensities of its bin pairs and stores them to every rank; 5. every rank copies
+   them out (``finish``).  Device-side barriers separate the steps; there is no
    NCCL collective on the path.  ``polarizability_ts`` all-gathers the series lazily when read.
 
 Without symmetric memory (CPU tensors, gloo, other backends) the local block is evaluated, one
@@ -129,6 +132,12 @@ class _SharedContext:
                    "rn_spectrum_dist_route")
         self.period, self.width = int(period.value), int(width.value)
         self.transform_ranks = self.period // self.width
+        stripe = ctypes.c_int64()
+        _lib.check(lib.rn_spectrum_dist_stripe(self.plan, ctypes.byref(stripe)), "rn_spectrum_dist_stripe")
+        self.stripe = int(stripe.value)
+        self.phased = {}             # (model id, block pointer) -> every rank can evaluate in two phases
+        self.packed_generation = -1  # generation whose first pack half is already running on the side stream
+        self.pack_event = None
 
         def align(nbytes: int) -> int:
             return (nbytes + 255) // 256 * 256
@@ -153,6 +162,12 @@ class _SharedContext:
             raise SymmetricMemoryUnavailable(str(getattr(self, "error", "another rank could not allocate symmetric memory")))
         self.generation = 0
         self._side_streams = None
+        # RN_DIST_OVERLAP=1: evaluate in two launches and run the first half of the pack (NVLink-bound) on a
+        # second stream under the second launch (HBM-bound), module docstring step 1.  Measured on 4 x B200
+        # (1M LLZO frames per GPU): the spectrum stage drops from 0.445 to 0.394 ms as intended, but the
+        # evaluation in two launches with a barrier between them costs 0.94 instead of 0.85 ms — 1.322 against
+        # 1.281 ms per step, whichever kernel is enqueued first — so it is off by default.
+        self.overlap = os.environ.get("RN_DIST_OVERLAP", "0") == "1"
         # RN_DIST_PIPELINE=1: one stream per packed sequence (pack -> barrier -> convolution), so that the
         # NVLink-bound stores of one sequence can overlap the FP64-bound passes of another.  Measured on
         # 4 x B200 (1M frames per GPU): 1.254 ms/step against 1.262 ms with one launch for the three
@@ -182,6 +197,14 @@ class _SharedContext:
         if self._side_streams is None:
             self._side_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(2)]
         return self._side_streams
+
+    def pack_stream(self, device):
+        """The stream of the overlapped first pack half (default priority, see ShardedTrajectory)."""
+        import torch  # pylint: disable=import-outside-toplevel
+
+        if getattr(self, "_pack_stream", None) is None:
+            self._pack_stream = torch.cuda.Stream(device=device)
+        return self._pack_stream
 
     def close(self) -> None:
         if getattr(self, "plan", None):
@@ -330,7 +353,7 @@ class ShardedMDRamanSpectrum(MDRamanSpectrum):
                     with torch.cuda.stream(lane):
                         lane_stream = ctypes.c_void_p(lane.cuda_stream)
                         _lib.check(lib.rn_spectrum_dist_pack(ctx.plan, series_ptr, ctx.table("work", group),
-                                                             ctx.table("spectrum", ctx.world), ctx.world, seq,
+                                                             ctx.table("spectrum", ctx.world), ctx.world, seq, -1,
                                                              lane_stream), "rn_spectrum_dist_pack")
                         packed = torch.cuda.Event()
                         packed.record(lane)
@@ -344,9 +367,15 @@ class ShardedMDRamanSpectrum(MDRamanSpectrum):
                 for done in finished:
                     current.wait_event(done)
             else:
+                # the first half of the pack may already be under way (ShardedTrajectory overlapped it with the
+                # evaluation of the frames the second half needs)
+                half_done = ctx.packed_generation == self._generation
+                if half_done:
+                    torch.cuda.current_stream(device).wait_event(ctx.pack_event)
+                    ctx.packed_generation = -1  # the transform runs in place: a second measure() packs everything
                 _lib.check(lib.rn_spectrum_dist_pack(ctx.plan, series_ptr, ctx.table("work", group),
-                                                     ctx.table("spectrum", ctx.world), ctx.world, -1, stream),
-                           "rn_spectrum_dist_pack")
+                                                     ctx.table("spectrum", ctx.world), ctx.world, -1,
+                                                     1 if half_done else -1, stream), "rn_spectrum_dist_pack")
                 ctx.barrier()  # every residue of every block has landed in the work buffers
                 _lib.check(lib.rn_spectrum_dist_transform(ctx.plan, work_ptr, ctx.table("recv", group), -1, stream),
                            "rn_spectrum_dist_transform")
@@ -425,6 +454,20 @@ class ShardedTrajectory(Dynamics):
         bounds = shard_bounds(self._num_frames, dist.get_world_size(self._group), dist.get_rank(self._group))
         return ShardedMDRamanSpectrum(full, self._local.timestep, self._group, bounds=bounds)
 
+    def _phased(self, ctx, model, positions, start: int) -> bool:
+        """True if EVERY rank can evaluate its block in the two phases of the overlapped schedule (decided
+        once per model and block: the answer is a collective)."""
+        if not ctx.overlap or ctx.stripe <= 0 or ctx.pipeline or not hasattr(positions, "data_ptr"):
+            return False
+        supported = getattr(model, "routed_phases_supported", None)
+        if supported is None:
+            return False
+        key = (id(model), int(positions.data_ptr()), tuple(positions.shape))
+        if key not in ctx.phased:
+            ctx.phased.clear()
+            ctx.phased[key] = _all_ranks_agree(bool(supported(positions, start, ctx.stripe)), ctx.device, self._group)
+        return ctx.phased[key]
+
     def _get_raman_spectrum_shared(self, polarizability_model):
         import torch  # pylint: disable=import-outside-toplevel
         import torch.distributed as dist  # pylint: disable=import-outside-toplevel
@@ -442,11 +485,40 @@ class ShardedTrajectory(Dynamics):
             return None
         start, stop = shard_bounds(self._num_frames, world, rank)
         peers = [0 if r == rank else ctx.ptr(r, "series") for r in range(world)]
+        local_ptr = ctx.ptr(rank, "series") + start * 72
+        phased = self._phased(ctx, polarizability_model, positions, start)
+        generation = ctx.generation + 1
+        if ctx.pack_event is not None:  # a first pack half that no measure() waited for still reads the buffers
+            torch.cuda.current_stream(device).wait_event(ctx.pack_event)
+            ctx.pack_event = None
         try:
-            routed(positions, ctx.ptr(rank, "series") + start * 72, peers, start, ctx.period, ctx.width)
+            if phased:
+                # Two launches: first the frames the first half of every rank's pack reads, then the others.  After
+                # a barrier the pack's first half (NVLink-bound) runs on a side stream under the second launch
+                # (HBM-bound); ``measure`` packs the other half.
+                routed(positions, local_ptr, peers, start, ctx.period, ctx.width, stripe=ctx.stripe, phase=0)
+                ctx.barrier()  # the rows of the first halves have landed on every rank
+                current = torch.cuda.current_stream(device)
+                landed = torch.cuda.Event()
+                landed.record(current)
+                # the evaluation is enqueued FIRST and the pack stream has no priority over it: the evaluation's
+                # CTAs (one per SM, most of its shared memory) are placed first and the pack's CTAs fill in beside
+                # them — the other way round the pack's thousand small CTAs occupy the SMs and the evaluation waits
+                routed(positions, local_ptr, peers, start, ctx.period, ctx.width, stripe=ctx.stripe, phase=1)
+                side = ctx.pack_stream(device)
+                side.wait_event(landed)
+                group = ctx.transform_ranks
+                _lib.check(_lib.lib().rn_spectrum_dist_pack(
+                    ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "series")), ctx.table("work", group),
+                    ctx.table("spectrum", world), world, -1, 0, ctypes.c_void_p(side.cuda_stream)), "rn_spectrum_dist_pack")
+                ctx.pack_event = torch.cuda.Event()
+                ctx.pack_event.record(side)
+                ctx.packed_generation = generation
+            else:
+                routed(positions, local_ptr, peers, start, ctx.period, ctx.width)
         except ValueError as exc:
             raise ValueError("polarizability_model and trajectory are incompatible") from exc
-        ctx.generation += 1
+        ctx.generation = generation
         ctx.barrier()  # every rank's rows have landed where they are consumed
         return ShardedMDRamanSpectrum(None, self._local.timestep, self._group, context=ctx,
                                       generation=ctx.generation, bounds=(start, stop))

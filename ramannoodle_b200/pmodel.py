@@ -274,13 +274,29 @@ class InterpolationModel(PolarizabilityModel):
         _lib.check(status, "rn_calc_polarizabilities_host_multi")
 
     # pylint: disable=too-many-arguments,too-many-positional-arguments
+    def routed_phases_supported(self, positions_batch, first_frame: int, stripe: int) -> bool:
+        """Whether ``calc_polarizabilities_routed(..., stripe=stripe, phase=0|1)`` can evaluate this block
+        (``rn_routed_phases_supported``: a purely linear model on the TMA path, HBM-resident 16-byte aligned
+        rows, block bounds on multiples of 16 frames)."""
+        if stripe <= 0 or not _is_torch_tensor(positions_batch) or not positions_batch.is_cuda:
+            return False
+        import torch  # pylint: disable=import-outside-toplevel
+
+        if positions_batch.dtype != torch.float64 or not positions_batch.is_contiguous() or self.is_dummy_model:
+            return False
+        native = self._native_model(self._resolve_device(positions_batch))
+        return bool(_lib.lib().rn_routed_phases_supported(native.handle, ctypes.c_void_p(positions_batch.data_ptr()),
+                                                          int(positions_batch.shape[0]), int(first_frame), int(stripe)))
+
     def calc_polarizabilities_routed(self, positions_batch, local_ptr: int, peer_series, first_frame: int,
-                                     period: int, width: int) -> None:
+                                     period: int, width: int, stripe: int = 0, phase: int = -1) -> None:
         """Evaluate this rank's block and route the rows for the shared multi-GPU spectrum
         (``rn_calc_polarizabilities_routed``): rows go to ``local_ptr`` (this rank's block inside its own
         full series buffer) and, written by the kernels over NVLink, to the series buffers
         ``peer_series[r]`` (base pointers, 0 for this rank) of the ranks whose spectrum stage consumes them —
-        row ``n`` to ranks ``(n % period) // width`` and ``((n - 1) % period) // width``."""
+        row ``n`` to ranks ``(n % period) // width`` and ``((n - 1) % period) // width``.
+        ``phase`` 0 / 1 (with ``stripe``; CUDA tensors only, ``routed_phases_supported``): one half of the
+        pipelined schedule, ``rn_calc_polarizabilities_routed_phase``."""
         import torch  # pylint: disable=import-outside-toplevel
 
         world = len(peer_series)
@@ -298,11 +314,19 @@ class InterpolationModel(PolarizabilityModel):
             native = self._native_model(device)
             with torch.cuda.device(device):
                 stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-                status = _lib.lib().rn_calc_polarizabilities_routed(
-                    native.handle, ctypes.c_void_p(data.data_ptr()), int(data.shape[0]), ctypes.c_void_p(int(local_ptr)),
-                    peers, world, int(first_frame), int(period), int(width), stream)
+                if phase >= 0:
+                    status = _lib.lib().rn_calc_polarizabilities_routed_phase(
+                        native.handle, ctypes.c_void_p(data.data_ptr()), int(data.shape[0]),
+                        ctypes.c_void_p(int(local_ptr)), peers, world, int(first_frame), int(period), int(width),
+                        int(stripe), int(phase), stream)
+                else:
+                    status = _lib.lib().rn_calc_polarizabilities_routed(
+                        native.handle, ctypes.c_void_p(data.data_ptr()), int(data.shape[0]),
+                        ctypes.c_void_p(int(local_ptr)), peers, world, int(first_frame), int(period), int(width), stream)
             _lib.check(status, "rn_calc_polarizabilities_routed")
             return
+        if phase >= 0:
+            raise ValueError("phased evaluation needs an HBM-resident trajectory block")
         if not isinstance(positions_batch, np.ndarray):
             raise get_type_error("positions", positions_batch, "ndarray")
         if positions_batch.ndim != 3 or positions_batch.shape[1:] != (self.num_atoms, 3):

@@ -268,8 +268,20 @@ def md_intensities(alpha, world: int = 1):
     return (power[k] + power[m_len - k]) * (0.25 / (float(big) * float(big))) + 0.5 * energy
 
 
+def mirror_half_slots(log2w: int) -> int:
+    return (1 << (log2w - 1)) + 64
+
+
+def mirror_arcs(owner: int, c: int, log2lh: int, log2w: int):
+    """csrc/rn_fft.cuh: mirror_arcs — 32-aligned origin of the owner's ascending half, top (31 mod 32) of its
+    descending half."""
+    lh = 1 << log2lh
+    a0 = (owner << log2w) + (c & 1)
+    return (((c + a0) >> 1) & (lh - 1)) & ~31, (((2 * lh + c - a0) >> 1) & (lh - 1)) | 31
+
+
 def mirror_owner(m1: int, c: int, log2lh: int, log2w: int, world: int):
-    """csrc/rn_fft.cuh: mirror_owner — (owner rank, slot in the owner's slice of w + 2 slots) of residue m1."""
+    """csrc/rn_fft.cuh: mirror_owner — (owner rank, slot in the owner's slice of 2 * mirror_half_slots slots)."""
     lh = 1 << log2lh
     u = 2 * m1 - c
     if u < 0:
@@ -277,7 +289,10 @@ def mirror_owner(m1: int, c: int, log2lh: int, log2w: int, world: int):
     far_side = u > lh
     a = 2 * lh - u if far_side else u
     owner = min(a >> log2w, world - 1)
-    return owner, ((a - (owner << log2w)) >> 1) + (((1 << (log2w - 1)) + 1) if far_side else 0)
+    near_origin, far_top = mirror_arcs(owner, c, log2lh, log2w)
+    if far_side:
+        return owner, mirror_half_slots(log2w) + ((far_top - m1) & (lh - 1))
+    return owner, (m1 - near_origin) & (lh - 1)
 
 
 def final_pairs(rank: int, num_bins: int, log2lh: int, world: int):
@@ -295,6 +310,9 @@ def final_pairs(rank: int, num_bins: int, log2lh: int, world: int):
             continue
         m_near = ((a + c) >> 1) & (lh - 1)
         m_far = ((2 * lh + c - a) >> 1) & (lh - 1)
+        near_origin, far_top = mirror_arcs(rank, c, log2lh, log2w)
+        near_slot = (m_near - near_origin) & (lh - 1)
+        far_slot = mirror_half_slots(log2w) + ((far_top - m_far) & (lh - 1))
         bins = []
         for q in range(world // 2):
             m = q * lh + m_near
@@ -305,5 +323,5 @@ def final_pairs(rank: int, num_bins: int, log2lh: int, world: int):
             if k > points:
                 continue
             bins.append((k, m, m2, m2 >> log2lh))
-        out.append((local, local + half + 1, m_near, m_far, bins))
+        out.append((near_slot, far_slot, m_near, m_far, bins))
     return out

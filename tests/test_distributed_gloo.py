@@ -154,3 +154,34 @@ def test_allgather_series_world2(frames):
         proc.join(timeout=60)
         assert proc.exitcode == 0
     assert sorted(results) == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("num_frames, first_frame, stripe", [(1_000_000, 3_000_000, 131072), (1_000_000, 0, 262144),
+                                                             (147_456, 294_912, 65536), (16, 2048, 1024),
+                                                             (4096, 1024 * 7 + 16, 1024)])
+def test_phase_tile_selection_partitions_the_block(num_frames, first_frame, stripe):
+    """The two launches of the overlapped multi-GPU schedule (rn_calc_polarizabilities_routed_phase) between them
+    evaluate every 16-frame tile of a block exactly once, phase 0 exactly the frames n with
+    (n mod 2*stripe) < stripe + 16 — every row the first half of any rank's pack reads (difference signal n
+    needs rows n and n + 1, n mod 2*stripe < stripe) — in increasing order (host arithmetic of the native library)."""
+    import ctypes
+
+    from ramannoodle_b200 import _lib
+
+    lib = _lib.lib()
+    tiles = num_frames // 16
+    selected = []
+    for phase in (0, 1):
+        buffer = (ctypes.c_int64 * tiles)()
+        count = lib.rn_debug_phase_tiles(num_frames, first_frame, stripe, phase, buffer, tiles)
+        assert 0 <= count <= tiles
+        chosen = list(buffer[:count])
+        assert chosen == sorted(chosen)
+        selected.append(chosen)
+        for tile in chosen:
+            early = ((first_frame + 16 * tile) % (2 * stripe)) < stripe + 16
+            assert early == (phase == 0)
+    assert sorted(selected[0] + selected[1]) == list(range(tiles))
+    needed = {(n - first_frame) // 16 for n in range(first_frame, first_frame + num_frames)
+              if n % (2 * stripe) < stripe or (n - 1) % (2 * stripe) < stripe} if num_frames <= 200_000 else set()
+    assert needed <= set(selected[0])

@@ -66,8 +66,9 @@ def test_measure_model_matches_oracle(frames, world):
     assert np.abs(got / ref - 1).max() < 1e-11
 
 
-@pytest.mark.parametrize("num_bins, log2lh, world", [(40, 6, 2), (41, 6, 2), (100, 6, 4), (127, 6, 4), (128, 6, 4),
-                                                     (255, 6, 8), (256, 6, 8), (250, 6, 8), (8999, 12, 8), (8000, 12, 4)])
+@pytest.mark.parametrize("num_bins, log2lh, world", [(300, 10, 2), (513, 10, 2), (1100, 10, 4), (2047, 10, 4),
+                                                     (2048, 10, 4), (4095, 10, 8), (4096, 10, 8), (3330, 10, 8),
+                                                     (8999, 12, 8), (8000, 12, 4)])
 def test_mirror_ownership_of_shared_transform(num_bins, log2lh, world):
     """Index logic of the shared transform's last two steps (store_out's mirror_owner and the pair
     enumeration of final_dist_kernel), restated in tests/fft_model.py: every residue has exactly one
@@ -81,7 +82,10 @@ def test_mirror_ownership_of_shared_transform(num_bins, log2lh, world):
     seen = {}
     for m1 in range(lh):
         owner, slot = fm.mirror_owner(m1, c, log2lh, log2w, world)
-        assert 0 <= owner < world and 0 <= slot < w + 2
+        assert 0 <= owner < world and 0 <= slot < 2 * fm.mirror_half_slots(log2w)
+        far = slot >= fm.mirror_half_slots(log2w)
+        # aligned runs of 32 residues land in one aligned block of 32 slots, ascending or descending
+        assert (slot - fm.mirror_half_slots(log2w) if far else slot) % 32 == ((31 - m1 % 32) if far else m1 % 32)
         assert (owner, slot) not in seen
         seen[(owner, slot)] = m1
         mirror = (c - m1) % lh

@@ -30,11 +30,13 @@ def _run_check(world):
     with open(os.path.join(REPO, "gpurun_out", f"check_sharded_n{world}.log"), "w", encoding="utf-8") as log:
         log.write(res.stdout + "\n--- stderr ---\n" + res.stderr)
     assert res.returncode == 0, res.stdout[-6000:] + res.stderr[-6000:]
-    # 3 small cases x (host | HBM-resident) x (shared transform | all-gather) + 1 large case, per rank
-    assert res.stdout.count("ok=True") == world * 13 and "ok=False" not in res.stdout, res.stdout[-6000:]
+    # 3 small cases x (host | HBM-resident) x (shared transform | all-gather) + 2 large cases, per rank
+    assert res.stdout.count("ok=True") == world * 14 and "ok=False" not in res.stdout, res.stdout[-6000:]
     # the shared transform really ran (not the all-gather fallback)
     assert res.stdout.count("shared=True (used=True)") == world * 6
-    assert res.stdout.count("resident shared (used=True)") == world
+    assert res.stdout.count("resident shared (used=True)") == 2 * world
+    # ... and the aligned large case took the schedule that overlaps the first pack half with the evaluation
+    assert res.stdout.count("overlapped=True") == world
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")

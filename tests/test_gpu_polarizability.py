@@ -273,3 +273,38 @@ def test_dense_row_alignment_and_variants(structure, offset, variant):
     finally:
         hook(4, 0)
     assert rel_err(got, want) <= ALPHA_RTOL
+
+
+@pytest.mark.parametrize("first_tile, tiles, stripe", [(37, 300, 1024), (0, 1000, 2048), (129, 100, 1024)])
+def test_routed_evaluation_in_two_phases(first_tile, tiles, stripe):
+    """rn_calc_polarizabilities_routed_phase: phases 0 and 1 together store exactly what the one-launch
+    routed evaluation stores — locally and in the (here: emulated, same GPU) series buffers of both ranks."""
+    lib = _lib.lib()
+    frames, first = 16 * tiles, 16 * first_tile
+    state = synthetic.make_model("LLZO", "art")
+    model = rb.ARTModel(state)
+    positions = to_cuda(synthetic.make_trajectory("LLZO", frames, seed=3, lattice_hops=True))
+    total = first + frames + 64
+    assert model.routed_phases_supported(positions, first, stripe)
+    assert not model.routed_phases_supported(positions, first + 8, stripe)
+    results = []
+    for phased in (False, True):
+        series = [torch.full((total * 9,), float("nan"), dtype=torch.float64, device="cuda:0") for _ in range(2)]
+        local_ptr = series[0].data_ptr() + first * 72
+        peers = [0, series[1].data_ptr()]
+        if phased:
+            for phase in (1, 0):
+                model.calc_polarizabilities_routed(positions, local_ptr, peers, first, 2 * stripe, stripe,
+                                                   stripe=stripe, phase=phase)
+        else:
+            model.calc_polarizabilities_routed(positions, local_ptr, peers, first, 2 * stripe, stripe)
+        torch.cuda.synchronize()
+        results.append([t.cpu().numpy() for t in series])
+    for plain, phased in zip(*results):
+        assert np.array_equal(plain, phased, equal_nan=True)
+    local = results[1][0].reshape(total, 9)[first:first + frames]
+    assert not np.isnan(local).any()
+    want = ora.calc_polarizabilities(oracle_model(state), positions[:256].cpu().numpy())
+    assert rel_err(local[:256].reshape(-1, 3, 3), want) <= ALPHA_RTOL
+    hits = lib.rn_debug_phase_tiles(frames, first, stripe, 0, (ctypes.c_int64 * 1)(), 1)
+    assert 0 < hits < tiles

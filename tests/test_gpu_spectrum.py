@@ -242,10 +242,15 @@ def _emulated_shared_measure(alpha, timestep, world, by_sequence=False, **correc
             return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
         # all three sequences in one launch, or one sequence per launch (what the pipelined schedule does)
+        stripe = ctypes.c_int64()
+        assert lib.rn_spectrum_dist_stripe(plans[0], ctypes.byref(stripe)) == 0
+        # ... and, where the blocks are large enough, the pack in the two halves of the overlapped schedule
+        phases = (1, 0) if (stripe.value > 0 and not by_sequence) else (-1,)
         for seq in ((-1,) if not by_sequence else (2, 0, 1)):
             for rank in range(world):
-                assert lib.rn_spectrum_dist_pack(plans[rank], ctypes.c_void_p(d_alpha.data_ptr()), table(work[:group]),
-                                                 table(spec), world, seq, stream) == 0
+                for phase in phases:
+                    assert lib.rn_spectrum_dist_pack(plans[rank], ctypes.c_void_p(d_alpha.data_ptr()),
+                                                     table(work[:group]), table(spec), world, seq, phase, stream) == 0
             for rank in range(world):
                 assert lib.rn_spectrum_dist_transform(plans[rank], ctypes.c_void_p(work[rank].data_ptr()),
                                                       table(recv[:group]), seq, stream) == 0

@@ -49,30 +49,38 @@ for structure, kind, frames in (("LLZO", "art", 5001), ("STO", "cubic", 1237), (
         print(f"rank {rank}/{world} {structure}/{kind} S={frames} resident={resident} shared={shared} (used={used}): "
               f"alpha {e_a:.1e} intensity {e_i:.1e} ok={good}", flush=True)
 
-# large case: strided levels in the local transforms, rows routed across many tiles
+# large cases: strided levels in the local transforms, rows routed across many tiles.  The first has an uneven
+# tail; the blocks of the second start and end on multiples of 16 frames, which lets the evaluation run in two
+# phases with the first half of the pack overlapped (the overlapped schedule must have been used there).
 state = synthetic.make_model("LLZO", "art")
 model = rb.ARTModel(state, device=local)
-frames = big_frames + 7  # uneven tail
-start, stop = shard_bounds(frames, world, rank)
-block = synthetic.make_trajectory_cuda("LLZO", stop - start, device, seed=1000 + rank, first_frame=start)
-sharded = ShardedTrajectory(block, 0.5, frames)
-spectrum = sharded.get_raman_spectrum(model)
-wn, inten = spectrum.measure_device(laser_correction=True, laser_wavelength=532)
-series = spectrum._gathered()  # pylint: disable=protected-access
-# reference: the gathered trajectory through the single-GPU path on this rank
-per = -(-frames // world)
-padded = torch.zeros((per,) + tuple(block.shape[1:]), dtype=torch.float64, device=device)
-padded[: stop - start] = sharded.local._positions_ts  # pylint: disable=protected-access
-full = torch.empty((world * per,) + tuple(block.shape[1:]), dtype=torch.float64, device=device)
-dist.all_gather_into_tensor(full, padded)
-single = rb.Trajectory(full[:frames], 0.5).get_raman_spectrum(model)
-swn, sint = single.measure_device(laser_correction=True, laser_wavelength=532)
-e_a = float((series - single._polarizability_ts).abs().max() / single._polarizability_ts.abs().max())  # pylint: disable=protected-access
-e_i = float(((inten - sint).abs() / sint.abs()).max())
-good = e_a <= 1e-13 and e_i <= 1e-10 and bool(torch.equal(wn, swn))
-ok = ok and good
-print(f"rank {rank}/{world} LLZO/art S={frames} resident shared (used={spectrum._context is not None}): "  # pylint: disable=protected-access
-      f"alpha {e_a:.1e} intensity {e_i:.1e} vs single GPU ok={good}", flush=True)
+for frames, overlapped in ((big_frames + 7, False), (world * 16 * (big_frames // (16 * world)), True)):
+    os.environ["RN_DIST_OVERLAP"] = "1" if overlapped else "0"  # read when the shared context of this size is created
+    start, stop = shard_bounds(frames, world, rank)
+    block = synthetic.make_trajectory_cuda("LLZO", stop - start, device, seed=1000 + rank, first_frame=start)
+    sharded = ShardedTrajectory(block, 0.5, frames)
+    spectrum = sharded.get_raman_spectrum(model)
+    ctx = spectrum._context  # pylint: disable=protected-access
+    was_overlapped = ctx is not None and ctx.packed_generation == ctx.generation
+    wn, inten = spectrum.measure_device(laser_correction=True, laser_wavelength=532)
+    wn_again, inten_again = spectrum.measure_device(laser_correction=True, laser_wavelength=532)  # packs everything anew
+    series = spectrum._gathered()  # pylint: disable=protected-access
+    # reference: the gathered trajectory through the single-GPU path on this rank
+    per = -(-frames // world)
+    padded = torch.zeros((per,) + tuple(block.shape[1:]), dtype=torch.float64, device=device)
+    padded[: stop - start] = sharded.local._positions_ts  # pylint: disable=protected-access
+    full = torch.empty((world * per,) + tuple(block.shape[1:]), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(full, padded)
+    single = rb.Trajectory(full[:frames], 0.5).get_raman_spectrum(model)
+    swn, sint = single.measure_device(laser_correction=True, laser_wavelength=532)
+    e_a = float((series - single._polarizability_ts).abs().max() / single._polarizability_ts.abs().max())  # pylint: disable=protected-access
+    e_i = float(((inten - sint).abs() / sint.abs()).max())
+    good = (e_a <= 1e-13 and e_i <= 1e-10 and bool(torch.equal(wn, swn)) and bool(torch.equal(inten, inten_again))
+            and was_overlapped == overlapped)
+    ok = ok and good
+    print(f"rank {rank}/{world} LLZO/art S={frames} resident shared (used={ctx is not None}) overlapped={was_overlapped}: "
+          f"alpha {e_a:.1e} intensity {e_i:.1e} vs single GPU ok={good}", flush=True)
+    del block, sharded, spectrum, series, padded, full, single
 
 flag = torch.tensor([1 if ok else 0], device=device)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)

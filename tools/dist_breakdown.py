@@ -44,7 +44,7 @@ phases = {
                                                               start, ctx.period, ctx.width),
     "barrier_0": ctx.barrier,
     "pack": lambda: lib.rn_spectrum_dist_pack(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "series")), ctx.table("work", group),
-                                                 ctx.table("spectrum", world), world, -1, stream),
+                                                 ctx.table("spectrum", world), world, -1, -1, stream),
     "barrier_1": ctx.barrier,
     "transform": lambda: lib.rn_spectrum_dist_transform(ctx.plan, ctypes.c_void_p(ctx.ptr(rank, "work")), ctx.table("recv", group), -1, stream),
     "barrier_2": ctx.barrier,

@@ -91,7 +91,7 @@ static AffineSmemLayout affine_layout(int K, int kp, int mt, int stages) {
 // rows of the tile: the DMMA B fragments (8 tensor components) stay in registers, the 9th
 // component's column of G and the reference positions are read from smem tables; partial 3x3
 // tensors are combined through smem.
-template <int KP, int MT, int STAGES, bool WRAP>
+template <int KP, int MT, int STAGES, bool WRAP, bool SELECT>
 __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 1)
     affine_tma_kernel(const double* __restrict__ in, const double* __restrict__ ref, const double* __restrict__ G,
                       int64_t num_frames, int K, int row_stride, int stage_doubles, Alpha0 a0,
@@ -115,11 +115,12 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
     // the tiles of this launch: all of them, or the selection of one phase of the pipelined schedule (then
     // num_frames is a multiple of ROWS).  Two cursors walk this CTA's tiles: the one computed on, and the one
     // being fetched STAGES visits ahead.
-    const int64_t num_tiles = sel.period ? sel.count : (num_frames + ROWS - 1) / ROWS;
+    // (SELECT is a template parameter: the cursor arithmetic in the tile loop costs the plain launch 3-4 %)
+    const int64_t num_tiles = SELECT ? sel.count : (num_frames + ROWS - 1) / ROWS;
     const uint32_t row_bytes = (uint32_t)K * 8u;
 
     auto issue_tile = [&](int64_t tile, int s) {
-        const int64_t frame0 = select_tile(sel, tile) * ROWS;  // (prologue only: a division per call)
+        const int64_t frame0 = (SELECT ? select_tile(sel, tile) : tile) * ROWS;  // (prologue only: a division per call)
         const int rows = (int)min((int64_t)ROWS, num_frames - frame0);
         mbar_arrive_expect_tx(full0 + 8 * s, row_bytes * rows);
         const uint32_t dst0 = smem_u32(stages + (size_t)s * stage_doubles);
@@ -164,12 +165,13 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
     int64_t i = 0;
     int64_t pending_row0 = -1;  // first row of the tile that sits in outbuf waiting for its bulk stores
     TileCursor here, ahead;
-    cursor_set(sel, blockIdx.x, here);
-    cursor_set(sel, blockIdx.x + (int64_t)STAGES * gridDim.x, ahead);
-    for (int64_t tile = blockIdx.x; tile < num_tiles;
-         tile += gridDim.x, i++, cursor_advance(sel, gridDim.x, here), cursor_advance(sel, gridDim.x, ahead)) {
+    if (SELECT) {
+        cursor_set(sel, blockIdx.x, here);
+        cursor_set(sel, blockIdx.x + (int64_t)STAGES * gridDim.x, ahead);
+    }
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, i++) {
         const int s = (int)(i % STAGES);
-        const int64_t tile_row0 = cursor_tile(sel, here) * ROWS;
+        const int64_t tile_row0 = (SELECT ? cursor_tile(sel, here) : tile) * ROWS;
         // full tiles go to the peers as bulk stores; a partial last tile uses plain stores
         const bool stage_rows = peers_bulk && (tile_row0 + ROWS <= num_frames);
         mbar_wait(full0 + 8 * s, (uint32_t)(i / STAGES) & 1);
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
             // refill stage s: thread 0 arms the barrier, lane 0 of warp w copies rows w, w+8, ...
             const int64_t next = tile + (int64_t)STAGES * gridDim.x;
             if (next < num_tiles && lane == 0) {
-                const int64_t frame0 = cursor_tile(sel, ahead) * ROWS;
+                const int64_t frame0 = (SELECT ? cursor_tile(sel, ahead) : next) * ROWS;
                 const int rows = (int)min((int64_t)ROWS, num_frames - frame0);
                 if (warp == 0) mbar_arrive_expect_tx(full0 + 8 * s, row_bytes * rows);
                 const uint32_t dst0 = smem_u32(stages + (size_t)s * stage_doubles);
@@ -265,6 +267,10 @@ __global__ void __launch_bounds__(kAffineWarps * 32, (KP <= 9 && MT == 1) ? 2 : 
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         pending_row0 = stage_rows ? tile_row0 : -1;
+        if (SELECT) {
+            cursor_advance(sel, gridDim.x, here);
+            cursor_advance(sel, gridDim.x, ahead);
+        }
     }
     if (peers_bulk) {
         __syncthreads();
@@ -297,7 +303,7 @@ static int launch_affine_tma_cfg(const rn_model* m, const double* d_in, int64_t 
     if (tiles == 0) return RN_OK;
     const double* ref = WRAP ? m->d_ref_wrapped : m->d_zero_ref;
     const double* G = WRAP ? m->d_g_frac : m->d_g_cart;
-    auto kern = affine_tma_kernel<KP, MT, STAGES, WRAP>;
+    auto kern = sel.period ? affine_tma_kernel<KP, MT, STAGES, WRAP, true> : affine_tma_kernel<KP, MT, STAGES, WRAP, false>;
     RN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
     int ctas_per_sm = 1;
     RN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kAffineWarps * 32, L.bytes));

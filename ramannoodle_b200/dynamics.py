@@ -47,7 +47,7 @@ class Trajectory(Dynamics, Sequence):
         self._timestep = timestep
         self._pinned_owner = None
         if _is_torch_tensor(positions_ts):
-            self._positions_ts = self._wrap_device(positions_ts)
+            self._positions_ts = self._wrap_device(positions_ts, pin_memory)
         else:
             self._positions_ts = self._wrap_host(np.asarray(positions_ts), pin_memory)
 
@@ -65,12 +65,11 @@ class Trajectory(Dynamics, Sequence):
         self._positions_ts = positions
         return self
 
-    @staticmethod
-    def _wrap_device(tensor):
+    def _wrap_device(self, tensor, pin_memory: bool = True):
         import torch  # pylint: disable=import-outside-toplevel
 
-        if not tensor.is_cuda:
-            return Trajectory._wrap_host(tensor.numpy(), True)
+        if not tensor.is_cuda:  # a CPU tensor is host data: same path (and pinned owner) as an ndarray
+            return self._wrap_host(tensor.detach().cpu().numpy(), pin_memory)
         data = tensor.to(torch.float64).contiguous()
         out = torch.empty_like(data)
         device = int(data.device.index or 0)

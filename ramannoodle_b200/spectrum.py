@@ -8,6 +8,7 @@ types and error messages; the arithmetic runs in the CUDA library.
 from __future__ import annotations
 
 import ctypes
+import threading
 from collections import OrderedDict
 
 import numpy as np
@@ -62,11 +63,28 @@ class _Plan:
 
 
 _PLAN_CACHE: "OrderedDict[tuple, _Plan]" = OrderedDict()
-_PLAN_CACHE_SIZE = 2
+_PLAN_CACHE_SIZE = 4
+_PLAN_CACHE_LOCK = threading.Lock()
 
 
 def _get_plan(num_frames: int, device: int) -> _Plan:
-    key = (int(num_frames), int(device))
+    """A plan owns its work buffers, so it is shared only by calls that are ordered anyway: the same
+    Python thread AND the same CUDA stream (two streams or two threads measuring series of the same length
+    would otherwise race on the buffers)."""
+    stream_id = 0
+    try:
+        import torch  # pylint: disable=import-outside-toplevel
+
+        if torch.cuda.is_available():
+            stream_id = int(torch.cuda.current_stream(device).cuda_stream)
+    except (ImportError, RuntimeError):
+        stream_id = 0
+    key = (int(num_frames), int(device), stream_id, threading.get_ident())
+    with _PLAN_CACHE_LOCK:
+        return _get_plan_locked(key, num_frames, device)
+
+
+def _get_plan_locked(key, num_frames: int, device: int) -> _Plan:
     plan = _PLAN_CACHE.get(key)
     if plan is None:
         _lib.require_device(device)
@@ -81,9 +99,10 @@ def _get_plan(num_frames: int, device: int) -> _Plan:
 
 
 def clear_plan_cache() -> None:
-    while _PLAN_CACHE:
-        _, plan = _PLAN_CACHE.popitem()
-        plan.close()
+    with _PLAN_CACHE_LOCK:
+        while _PLAN_CACHE:
+            _, plan = _PLAN_CACHE.popitem()
+            plan.close()
 
 
 def get_bose_einstein_correction(wavenumbers, temperature):

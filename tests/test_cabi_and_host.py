@@ -174,3 +174,46 @@ def test_corrections_match_oracle():
     wn = np.linspace(1.0, 3500.0, 500)
     assert np.array_equal(rb.get_bose_einstein_correction(wn, 300), ora.get_bose_einstein_correction(wn, 300))
     assert np.array_equal(rb.get_laser_correction(wn, 1e7 / 532), ora.get_laser_correction(wn, 1e7 / 532))
+
+
+def test_trajectory_accepts_cpu_tensors():
+    """A CPU torch tensor is host data: wrapped like an ndarray (``_wrap_device`` called the
+    instance method ``_wrap_host`` unbound and raised TypeError)."""
+    import torch
+
+    positions = np.random.default_rng(0).uniform(-1.5, 2.5, size=(4, 5, 3))
+    trajectory = rb.Trajectory(torch.from_numpy(positions), 1.0, pin_memory=False)
+    assert not trajectory.is_device_resident
+    assert np.array_equal(np.asarray(trajectory.positions_ts), positions - positions // 1)
+
+
+def test_spectrum_plans_are_not_shared_across_threads():
+    """Plans own work buffers: the cache key includes the thread (and the CUDA stream), so two threads
+    measuring series of the same length never get the same plan object."""
+    import threading
+
+    from ramannoodle_b200 import spectrum
+
+    created = []
+
+    class FakePlan:
+        def __init__(self, num_frames, device):
+            created.append((num_frames, device, threading.get_ident()))
+
+        def close(self):
+            pass
+
+    original_plan, original_require = spectrum._Plan, _lib.require_device  # pylint: disable=protected-access
+    spectrum._Plan, _lib.require_device = FakePlan, lambda device=0: {}  # pylint: disable=protected-access
+    try:
+        spectrum.clear_plan_cache()
+        first = spectrum._get_plan(1000, 0)  # pylint: disable=protected-access
+        assert spectrum._get_plan(1000, 0) is first  # pylint: disable=protected-access
+        other = []
+        worker = threading.Thread(target=lambda: other.append(spectrum._get_plan(1000, 0)))  # pylint: disable=protected-access
+        worker.start()
+        worker.join()
+        assert other[0] is not first and len(created) == 2
+    finally:
+        spectrum._Plan, _lib.require_device = original_plan, original_require  # pylint: disable=protected-access
+        spectrum._PLAN_CACHE.clear()  # pylint: disable=protected-access

@@ -17,6 +17,10 @@ reasons = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not 
 by_op, by_reason, by_op_reason = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter)
 total = 0.0
 for r in rows[start + 1:]:
+    if r and r[0] == "Kernel Name":  # next captured launch
+        break
+    if len(r) < len(hdr):
+        continue
     try:
         v = float(r[cs] or 0)
     except (ValueError, IndexError):

@@ -10,12 +10,17 @@ rows = list(csv.DictReader(lines))
 names = [r["Kernel Name"] for r in rows]
 vals = [float(r["Metric Value"].replace(",", "")) for r in rows]
 idx = [i for i, n in enumerate(names) if anchor in n]
-seg = range(idx[-2], idx[-1])  # the last full step: anchor kernel -> next anchor kernel
+# a steady-state step: the most common anchor-to-anchor segment length (warm-up builds plans, the tail of a
+# bench run times stages separately), taken at its first repetition
+lengths = collections.Counter(b - a for a, b in zip(idx, idx[1:]))
+step_len = max(lengths, key=lambda n: (lengths[n], n))
+first = next(a for a, b in zip(idx[1:], idx[2:]) if b - a == step_len)
+seg = range(first, first + step_len)
 tot = collections.defaultdict(float)
 cnt = collections.Counter()
 for i in seg:
     n = re.sub(r"\(.*", "", names[i]).replace("void ", "").replace("rn::", "")
-    n = re.sub(r"<.*", "", n) if "fft_tile" not in n and "affine" not in n and "dense" not in n else n
+    n = re.sub(r"<.*", "", n) if not any(k in n for k in ("level_kernel", "tile_kernel", "affine", "dense", "pack_")) else n
     tot[n] += vals[i]
     cnt[n] += 1
 total = sum(tot.values())

@@ -8,8 +8,8 @@
 The text is parsed by the native library (mmap + a pool of threads running a correctly rounded
 decimal parser, so every value equals Python's ``float(token)``), straight into the caller's buffer
 (page-locked when ``read_trajectory`` runs on a GPU box, so the ``Trajectory`` streams to the device
-at full PCIe bandwidth).  Only direct-coordinate XDATCAR frames are handled (Cartesian frames raise
-``InvalidFileException``; the reference converts them, ``poscar.py:118-119``).  vasprun.xml files the
+at full PCIe bandwidth).  XDATCAR files with frames in Cartesian coordinates (VASP writes Direct) take a
+Python walk with the reference's own numpy calls (``poscar.py:118-119``).  vasprun.xml files the
 native tokenizer does not understand are re-read with the standard library's ElementTree under the
 reference's rules.
 """
@@ -36,15 +36,84 @@ def _checked_path(filepath) -> str:
     return path
 
 
+class _CartesianFrames(Exception):
+    """The native scan met a frame in Cartesian coordinates (the Python walk below converts those)."""
+
+
 def _scan(path: str):
     frames = ctypes.c_int64()
     atoms = ctypes.c_int64()
     lattice = np.zeros((3, 3))
     status = _lib.lib().rn_xdatcar_scan(path.encode(), ctypes.byref(frames), ctypes.byref(atoms),
                                         ctypes.c_void_p(lattice.ctypes.data))
+    if status == -3:  # RN_ERR_UNSUPPORTED
+        raise _CartesianFrames(_lib.last_error())
     if status != 0:
         raise InvalidFileException(_lib.last_error())
     return int(frames.value), int(atoms.value), lattice
+
+
+def _xdatcar_header_python(file):
+    """``(lattice, num_atoms)`` from the header lines of an XDATCAR file (``poscar.py:13-77``)."""
+    file.readline()
+    line = file.readline()
+    try:
+        scale_factor = float(line)
+    except ValueError as exc:
+        raise InvalidFileException(f"scale factor could not be parsed: {line}") from exc
+    rows = []
+    for _ in range(3):
+        line = file.readline()
+        try:
+            vector = np.array([float(item) for item in line.split()[0:3]])
+        except ValueError as exc:
+            raise InvalidFileException(f"lattice could not be parsed: {line}") from exc
+        if vector.shape != (3,):
+            raise InvalidFileException(f"lattice could not be parsed: {line}")
+        rows.append(vector)
+    symbols = file.readline().split()
+    if len(symbols) == 0:
+        raise InvalidFileException("no atom symbols found")
+    line = file.readline()
+    counts = line.split()
+    if len(counts) != len(symbols):
+        raise InvalidFileException(f"wrong number of ion counts: {len(counts)} != {len(symbols)}")
+    try:
+        num_atoms = sum(int(count) for count in counts)
+    except ValueError as exc:
+        raise InvalidFileException(f"could not parse counts: {line}") from exc
+    return np.array(rows) * scale_factor, num_atoms
+
+
+def _xdatcar_positions_python(path: str) -> np.ndarray:
+    """The reference's XDATCAR walk (``xdatcar.py:21-56``, ``poscar.py:13-119``), used for files whose frames
+    are in Cartesian coordinates — VASP writes Direct, so this is the rare path: each such frame becomes
+    ``positions @ np.linalg.inv(lattice)`` (``poscar.py:118-119``), the same numpy calls as the reference."""
+    positions_ts = []
+    with open(path, "r", encoding="utf-8") as file:
+        lattice, num_atoms = _xdatcar_header_python(file)
+        while True:
+            label = file.readline()
+            if len(label.strip()) == 0 or label[0].strip() == "":
+                break  # "missing first character in coordinate format": the end of the series
+            if label[0].lower() == "s":  # selective dynamics
+                label = file.readline()
+            cart_mode = label[:1].lower() == "c"
+            if not cart_mode and label[:1].lower() != "d":
+                raise InvalidFileException(f"unrecognized coordinate format: {label}")
+            positions = []
+            for _ in range(num_atoms):
+                line = file.readline()
+                try:
+                    position = [float(item) for item in line.split()[0:3]]
+                except ValueError as exc:
+                    raise InvalidFileException(f"positions could not be parsed: {line}") from exc
+                if len(position) != 3:
+                    raise InvalidFileException(f"positions could not be parsed: {line}")
+                positions.append(position)
+            frame = np.array(positions)
+            positions_ts.append(frame @ np.linalg.inv(lattice) if cart_mode else frame)
+    return np.array(positions_ts)
 
 
 def _scan_outcar(path: str):
@@ -85,7 +154,16 @@ def read_positions_ts(filepath, num_threads: int = 0, out: np.ndarray | None = N
     """Fractional positions time series (S,N,3) from a VASP XDATCAR file; ``wrap`` applies the
     periodic wrap ``x - x // 1`` while parsing (what ``Trajectory`` does to its input)."""
     path = _checked_path(filepath)
-    frames, atoms, _ = _scan(path)
+    try:
+        frames, atoms, _ = _scan(path)
+    except _CartesianFrames:
+        positions = _xdatcar_positions_python(path)
+        if wrap:
+            positions = positions - positions // 1
+        if out is not None and positions.shape == out.shape:
+            out[...] = positions
+            return out
+        return positions
     out = _output(out, frames, atoms)
     status = _lib.lib().rn_xdatcar_read(path.encode(), ctypes.c_void_p(out.ctypes.data), frames, atoms, num_threads,
                                         int(bool(wrap)))
@@ -96,7 +174,12 @@ def read_positions_ts(filepath, num_threads: int = 0, out: np.ndarray | None = N
 
 def read_lattice(filepath) -> np.ndarray:
     """Scaled lattice (3,3) of an XDATCAR file (rows are lattice vectors, Å)."""
-    return _scan(_checked_path(filepath))[2]
+    path = _checked_path(filepath)
+    try:
+        return _scan(path)[2]
+    except _CartesianFrames:
+        with open(path, "r", encoding="utf-8") as file:
+            return _xdatcar_header_python(file)[0]
 
 
 def read_outcar_positions_ts(filepath, num_threads: int = 0, out: np.ndarray | None = None, wrap: bool = False,
@@ -182,7 +265,10 @@ def read_trajectory(filepath, timestep: float | None = None, file_format: str = 
     if file_format == "xdatcar":
         if timestep is None:
             raise ValueError("timestep is required for xdatcar trajectories")
-        frames, atoms, _ = _scan(path)
+        try:
+            frames, atoms, _ = _scan(path)
+        except _CartesianFrames:  # rare: Cartesian frames go through the Python walk and the usual constructor
+            return Trajectory(read_positions_ts(path), timestep)
         owner, out = _pinned(frames, atoms)
         positions = read_positions_ts(path, num_threads=num_threads, out=out, wrap=True)
     elif file_format == "outcar":

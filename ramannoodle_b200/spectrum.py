@@ -286,10 +286,15 @@ def convolve_spectrum(wavenumbers, intensities, function: str = "gaussian", widt
     """Smear a spectrum (``ramannoodle/spectrum/utils.py:12-73``); same defaults, output grid
     and error messages.  Accepts numpy arrays (or CUDA tensors) and returns numpy arrays."""
     torch = _torch()
-    wn_host = wavenumbers.detach().cpu().numpy() if _is_torch_tensor(wavenumbers) else wavenumbers
     if out_wavenumbers is None:
-        min_wavenumber = np.min(wn_host) - 100
-        max_wavenumber = np.max(wn_host) + 100
+        if _is_torch_tensor(wavenumbers) and wavenumbers.is_cuda and wavenumbers.numel() > 0:
+            # the default grid needs two numbers, not a copy of the spectrum
+            low, high = (float(v) for v in torch.aminmax(wavenumbers))
+        else:
+            wn_host = wavenumbers.detach().cpu().numpy() if _is_torch_tensor(wavenumbers) else wavenumbers
+            low, high = np.min(wn_host), np.max(wn_host)
+        min_wavenumber = low - 100
+        max_wavenumber = high + 100
         num_samples = int(np.rint(max_wavenumber - min_wavenumber))
         out_wavenumbers = np.linspace(min_wavenumber, max_wavenumber, num_samples)
     verify_ndarray_shape("out_wavenumbers", out_wavenumbers, (None,))

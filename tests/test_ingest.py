@@ -105,11 +105,16 @@ def test_malformed_files(tmp_path):
     (tmp_path / "counts").write_text("\n".join(bad) + "\n")
     with pytest.raises(rio.InvalidFileException, match="wrong number of ion counts: 1 != 2"):
         rio.read_positions_ts(tmp_path / "counts")
-    # Cartesian frames are refused, a trailing blank line ends the series like in the reference
-    bad = [line.replace("Direct", "Cartesian") for line in text]
-    (tmp_path / "cart").write_text("\n".join(bad) + "\n")
-    with pytest.raises(rio.InvalidFileException, match="Cartesian"):
-        rio.read_positions_ts(tmp_path / "cart")
+    # Cartesian frames are converted like in the reference (poscar.py:118-119: positions @ inv(lattice)); a
+    # trailing blank line ends the series like in the reference
+    cart = [line.replace("Direct", "Cartesian") for line in text]
+    (tmp_path / "cart").write_text("\n".join(cart) + "\n")
+    direct = rio.read_positions_ts(good)
+    lattice = rio.read_lattice(good)
+    converted = rio.read_positions_ts(tmp_path / "cart")
+    assert converted.shape == direct.shape
+    assert np.array_equal(converted, np.array([frame @ np.linalg.inv(lattice) for frame in direct]))
+    assert np.array_equal(rio.read_positions_ts(tmp_path / "cart", wrap=True), converted - converted // 1)
     (tmp_path / "blank").write_text("\n".join(text) + "\n\n\n")
     assert rio.read_positions_ts(tmp_path / "blank").shape == (3, 4, 3)
     with pytest.raises(FileNotFoundError):

@@ -93,3 +93,24 @@ def test_vasprun_reader_matches_reference_live(ref, tmp_path):
         read_trajectory(malformed)
     with pytest.raises(rio.InvalidFileException, match="no trajectory found"):
         rio.read_vasprun_positions_ts(malformed)
+
+
+def test_cartesian_xdatcar_matches_reference_live(ref, tmp_path):
+    """XDATCAR frames in Cartesian coordinates: the reference converts them with
+    ``positions @ inv(lattice)`` (``io/vasp/poscar.py:118-119``); so does this package, bit for bit."""
+    from ramannoodle.io.vasp.xdatcar import read_positions_ts
+
+    from ramannoodle_b200 import io as rio
+
+    rng = np.random.default_rng(2)
+    lines = ["synthetic", "  1.5", "  4.0 0.1 0.0", "  0.0 4.2 0.2", "  0.3 0.0 3.9", " Ti O", " 1 2"]
+    for frame in range(5):
+        lines.append("Cartesian configuration= %d" % (frame + 1) if frame % 2 == 0 else "Direct configuration= %d" % (frame + 1))
+        for row in rng.uniform(-1.0, 7.0, size=(3, 3)):
+            lines.append("  " + " ".join(repr(float(x)) for x in row))
+    path = tmp_path / "XDATCAR_cart"
+    path.write_text("\n".join(lines) + "\n")
+    expected = read_positions_ts(path)
+    assert np.array_equal(rio.read_positions_ts(path), expected)
+    trajectory = rio.read_trajectory(path, 1.0)
+    assert np.array_equal(np.asarray(trajectory.positions_ts), expected - expected // 1)

@@ -5,7 +5,6 @@ import collections
 import os
 import re
 import subprocess
-import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(REPO, "ramannoodle_b200", "libramannoodle_b200.so")

@@ -127,3 +127,20 @@ def test_spglib_stand_in_registration(monkeypatch):
 
     assert spglib.get_symmetry is symmetry.get_symmetry
     monkeypatch.delitem(sys.modules, "spglib", raising=False)
+
+
+@live
+def test_full_model_through_reference_construction():
+    """tools/build_model_reference.py: a complete 324-DOF TiO2 ARTModel built by the reference's own ``add_art``
+    with the space-group search in place of spglib and the vectorised scans of ``construction.py``."""
+    import json
+    import subprocess
+    import sys
+
+    from helpers import REPO
+
+    res = subprocess.run([sys.executable, os.path.join(REPO, "tools", "build_model_reference.py"), "TiO2", "--art"],
+                         capture_output=True, text=True, timeout=600, cwd=REPO, check=False)
+    assert res.returncode == 0, res.stderr[-2000:]
+    report = json.loads(res.stdout.strip().splitlines()[-1])
+    assert report["dofs"] == 324 and report["operations"] == 288 and report["nonequivalent_atoms"] == 2
